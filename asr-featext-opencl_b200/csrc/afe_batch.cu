@@ -1,0 +1,489 @@
+// Batch extractor (afe_batch_*): planning, launch of the fused kernel K1, statistics finalize K2 and the normalise
+// pass K3, plus the corpus-CMVN exchange hooks of the Normalizer subsystem.
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "afe_internal.h"
+#include "afe_fused.cuh"
+#include "afe_nccl.h"
+
+namespace afe {
+
+// ------------------------------------------------------------------------------------------------ FFT tables
+void FftTables::build(int n2)
+{
+    release();
+    N2 = n2;
+    const int M = n2 / 2, R = M / 16;
+    std::vector<float2> a((size_t)R * 16), p((size_t)M / 2);
+    for (int l = 0; l < R; l++)
+        for (int k1 = 0; k1 < 16; k1++) {
+            const double ang = -2.0 * M_PI * (double)(l * k1) / (double)M;
+            a[(size_t)l * 16 + k1] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int k = 0; k < M / 2; k++) {
+        const double ang = -2.0 * M_PI * (double)k / (double)n2;
+        p[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    AFE_CUDA(cudaMalloc(&d_tw_a, a.size() * sizeof(float2)));
+    AFE_CUDA(cudaMalloc(&d_tw_p, p.size() * sizeof(float2)));
+    AFE_CUDA(cudaMemcpy(d_tw_a, a.data(), a.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    AFE_CUDA(cudaMemcpy(d_tw_p, p.data(), p.size() * sizeof(float2), cudaMemcpyHostToDevice));
+}
+void FftTables::release()
+{
+    if (d_tw_a) cudaFree(d_tw_a);
+    if (d_tw_p) cudaFree(d_tw_p);
+    d_tw_a = d_tw_p = nullptr;
+}
+
+void MelTables::release()
+{
+    if (d_edges) cudaFree(d_edges);
+    if (d_pairs) cudaFree(d_pairs);
+    if (d_dct) cudaFree(d_dct);
+    if (d_window) cudaFree(d_window);
+    if (d_window2) cudaFree(d_window2);
+    d_edges = nullptr; d_pairs = nullptr; d_dct = nullptr; d_window = nullptr; d_window2 = nullptr;
+    alpha_built = -1.f;
+}
+
+void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st)
+{
+    std::vector<int> edges; std::vector<float> filters, pairs, dct;
+    build_filters(d, alpha, edges, filters);
+    for (int i = 0; i + 1 < (int)edges.size(); i++)
+        if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
+    if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
+    build_mel_pairs(d, edges, filters, pairs);
+    if (!t.d_edges) AFE_CUDA(cudaMalloc(&t.d_edges, sizeof(int) * (d.nb + 2)));
+    if (!t.d_pairs) AFE_CUDA(cudaMalloc(&t.d_pairs, sizeof(float) * 2 * d.bins));
+    // pageable source + stream-ordered copy: cudaMemcpyAsync from pageable memory stages synchronously, safe with locals
+    AFE_CUDA(cudaMemcpyAsync(t.d_edges, edges.data(), sizeof(int) * (d.nb + 2), cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaMemcpyAsync(t.d_pairs, pairs.data(), sizeof(float) * 2 * d.bins, cudaMemcpyHostToDevice, st));
+    if (d.C > 0 && !t.d_dct) {
+        build_dct(d, dct);
+        AFE_CUDA(cudaMalloc(&t.d_dct, sizeof(float) * dct.size()));
+        AFE_CUDA(cudaMemcpyAsync(t.d_dct, dct.data(), sizeof(float) * dct.size(), cudaMemcpyHostToDevice, st));
+    }
+    AFE_CUDA(cudaStreamSynchronize(st));
+    t.alpha_built = alpha;
+}
+
+void upload_window(const Derived &d, const float *window, MelTables &t, cudaStream_t st)
+{
+    if (!t.d_window) AFE_CUDA(cudaMalloc(&t.d_window, sizeof(float) * d.W));
+    if (!t.d_window2) AFE_CUDA(cudaMalloc(&t.d_window2, sizeof(float2) * d.M));
+    std::vector<float> w2((size_t)d.N2, 0.f);
+    memcpy(w2.data(), window, sizeof(float) * d.W);
+    AFE_CUDA(cudaMemcpyAsync(t.d_window, window, sizeof(float) * d.W, cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaMemcpyAsync(t.d_window2, w2.data(), sizeof(float) * d.N2, cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------------------------------------------------ K2 / K3
+// stats record per group: [sum[w], sumsq[w], count, min[w], max[w]]  (4w+1 doubles)
+__global__ void k_reduce_partials(const double *__restrict__ partials, const int *__restrict__ tile_begin,
+                                  const double *__restrict__ counts, int width, double *__restrict__ stats)
+{
+    const int g = blockIdx.x, c = threadIdx.x;
+    if (c >= width) return;
+    double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+    for (int t = tile_begin[g]; t < tile_begin[g + 1]; t++) { // fixed order: deterministic
+        const double *p = partials + ((long long)t * width + c) * 4;
+        s0 += p[0]; s1 += p[1];
+        lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+    }
+    double *o = stats + (long long)g * (4 * width + 1);
+    o[c] = s0; o[width + c] = s1; o[2 * width + 1 + c] = lo; o[3 * width + 1 + c] = hi;
+    if (c == 0) o[2 * width] = counts[g];
+}
+
+// mean / scale per group and column (normalizercpu.cpp:31-66). With norm_after_dyn == 0 the reference normalises the
+// statics before the deltas are taken, which equals scaling delta columns by the static column's scale (mean 0).
+__global__ void k_finalize_stats(const double *__restrict__ stats, int width, int cols, int norm_type, int norm_after_dyn,
+                                 float *__restrict__ mean, float *__restrict__ scale)
+{
+    const int g = blockIdx.x, c = threadIdx.x;
+    if (c >= width) return;
+    const double *o = stats + (long long)g * (4 * width + 1);
+    const double n = o[2 * width];
+    const int src = norm_after_dyn ? c : (c % cols);
+    const double s = o[src], s2 = o[width + src];
+    const float mn = (float)o[2 * width + 1 + src], mx = (float)o[3 * width + 1 + src];
+    float m = (float)(s / n), sc = 1.f;
+    if (norm_type == AFE_NORM_CVN) sc = (float)sqrt((n - 1.0) / (s2 - s * (s / n)));
+    else if (norm_type == AFE_NORM_MINMAX) sc = 1.f / fmaxf(fabsf(mn - m), fabsf(mx - m));
+    if (!norm_after_dyn && c >= cols) m = 0.f;
+    mean[(long long)g * width + c] = m;
+    scale[(long long)g * width + c] = sc;
+}
+
+__global__ void k_normalize_tiles(float *__restrict__ out, const Tile *__restrict__ tiles, int width, int norm_type,
+                                  const float *__restrict__ mean, const float *__restrict__ scale)
+{
+    const Tile tl = tiles[blockIdx.x];
+    float *base = out + (tl.out_row0 + tl.t0) * (long long)width;
+    const float *m = mean + (long long)tl.group * width, *s = scale + (long long)tl.group * width;
+    const int n = tl.nout * width;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i % width;
+        const float v = base[i] - m[c];
+        base[i] = norm_type == AFE_NORM_CMN ? v : v * s[c];
+    }
+}
+
+static std::atomic<int> g_launches{0};
+int kernel_launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+} // namespace afe
+
+using namespace afe;
+
+// ================================================================================================== afe_batch
+struct afe_batch {
+    Derived d;
+    int device;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    FftTables fft;
+    MelTables mel;
+    float alpha = 1.f;
+    bool window_set = false;
+    int scope = AFE_STATS_REFERENCE_BLOCK, flags = 0;
+    // plan
+    int n_utts = 0, n_tiles = 0, n_groups = 0;
+    bool aligned = false;
+    std::vector<int64_t> sample_off, frame_off;
+    int64_t pcm_extent = 0;
+    Tile *d_tiles = nullptr;
+    int *d_tile_begin = nullptr;
+    double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    float *d_mean = nullptr, *d_scale = nullptr;
+    int tc_max = 0, nout_max = 0;
+    FusedSmem L{};
+    int last_launches = 0;
+    // host staging for run_host
+    int16_t *d_pcm_stage = nullptr; float *d_out_stage = nullptr;
+    size_t pcm_stage_bytes = 0, out_stage_bytes = 0;
+
+    explicit afe_batch(const afe_params &p, int dev) : d(p), device(dev) {}
+    void free_plan()
+    {
+        if (d_tiles) cudaFree(d_tiles);
+        if (d_tile_begin) cudaFree(d_tile_begin);
+        if (d_counts) cudaFree(d_counts);
+        if (d_partials) cudaFree(d_partials);
+        if (d_stats) cudaFree(d_stats);
+        if (d_mean) cudaFree(d_mean);
+        if (d_scale) cudaFree(d_scale);
+        d_tiles = nullptr; d_tile_begin = nullptr; d_counts = d_partials = d_stats = nullptr; d_mean = d_scale = nullptr;
+    }
+};
+
+static void check_fused_support(const Derived &d)
+{
+    if (d.N2 != 512 && d.N2 != 256)
+        throw Error("fused batch path supports 256/512-point FFTs (window_size 129..512); use the streaming object");
+    if (d.S % 2) throw Error("fused batch path needs an even shift");
+    if (d.dct_len > 16) throw Error("fused batch path supports ceps_len + c0 <= 16");
+    if (d.width > kFusedThreads) throw Error("fused batch path supports output width <= 128");
+    if (d.nb + 2 > 256) throw Error("fused batch path supports num_banks <= 254");
+}
+
+template <int N2> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+{
+    const Derived &d = b->d;
+    FusedArgs a{};
+    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles;
+    a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
+    a.edges = b->mel.d_edges; a.pairs = reinterpret_cast<const float2 *>(b->mel.d_pairs); a.dct = b->mel.d_dct;
+    a.partials = want_stats ? b->d_partials : nullptr;
+    a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
+    a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
+    a.q1 = (b->flags & AFE_BATCH_Q1_EXACT) && d.D > 0 ? 1 : 0;
+    a.use_tma = (b->aligned && !(b->flags & AFE_BATCH_NO_TMA) && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
+    if (!want_stats) a.stats_rows_mode = 0;
+    else if (!d.p.norm_after_dyn) a.stats_rows_mode = 2;
+    else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
+    a.tc_max = b->tc_max;
+    a.nz = std::min(16, (d.W + 2 * dev::FftCfg<N2>::R - 1) / (2 * dev::FftCfg<N2>::R));
+    float den1 = 0, den2 = 0;
+    for (int l = 1; l <= d.l1; l++) den1 += l * l;   // float accumulation like deltacpu.cpp:26
+    for (int l = 1; l <= d.l2; l++) den2 += l * l;
+    a.den1 = 2 * den1; a.den2 = 2 * den2;
+    const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
+    auto kern = fast ? k_fused_mfcc<N2, true> : k_fused_mfcc<N2, false>;
+    AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
+    kern<<<b->n_tiles, kFusedThreads, b->L.total, b->stream>>>(a, b->L);
+    AFE_CUDA(cudaGetLastError());
+    count_launch();
+    b->last_launches++;
+}
+
+static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
+{
+    if (!b->window_set) throw Error("set_window must be called before running");
+    if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
+    if (b->mel.alpha_built != b->alpha) upload_mel_tables(b->d, b->alpha, b->mel, b->stream);
+    b->last_launches = 0;
+    const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
+    if (b->d.N2 == 512) launch_fused<512>(b, d_pcm, d_out, want_stats);
+    else launch_fused<256>(b, d_pcm, d_out, want_stats);
+}
+
+static void run_reduce(afe_batch *b)
+{
+    k_reduce_partials<<<b->n_groups, 128, 0, b->stream>>>(b->d_partials, b->d_tile_begin, b->d_counts, b->d.width, b->d_stats);
+    AFE_CUDA(cudaGetLastError());
+    count_launch(); b->last_launches++;
+}
+
+static void run_normalize(afe_batch *b, float *d_out)
+{
+    const Derived &d = b->d;
+    k_finalize_stats<<<b->n_groups, 128, 0, b->stream>>>(b->d_stats, d.width, d.cols, d.p.norm, d.p.norm_after_dyn,
+                                                        b->d_mean, b->d_scale);
+    AFE_CUDA(cudaGetLastError());
+    k_normalize_tiles<<<b->n_tiles, 256, 0, b->stream>>>(d_out, b->d_tiles, d.width, d.p.norm, b->d_mean, b->d_scale);
+    AFE_CUDA(cudaGetLastError());
+    count_launch(2); b->last_launches += 2;
+}
+
+extern "C" {
+
+int afe_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error(std::string("CUDA error: ") + cudaGetErrorString(e)); return 0; }
+    return n;
+}
+
+int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out)
+{
+    *out = nullptr;
+    return guarded([&] {
+        if (afe_device_count() <= cuda_device) throw Error("no usable CUDA device " + std::to_string(cuda_device) + " (the product has no CPU fallback)");
+        std::unique_ptr<afe_batch> b(new afe_batch(*p, cuda_device));
+        check_fused_support(b->d);
+        DeviceGuard g(cuda_device);
+        AFE_CUDA(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+        b->stream = b->own_stream;
+        b->fft.build(b->d.N2);
+        *out = b.release();
+    });
+}
+
+void afe_batch_destroy(afe_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    b->free_plan();
+    b->fft.release(); b->mel.release();
+    if (b->d_pcm_stage) cudaFree(b->d_pcm_stage);
+    if (b->d_out_stage) cudaFree(b->d_out_stage);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    delete b;
+}
+
+int afe_batch_set_window(afe_batch *b, const float *window)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        upload_window(b->d, window, b->mel, b->stream);
+        b->window_set = true;
+    });
+}
+
+int afe_batch_set_alpha(afe_batch *b, float alpha) { b->alpha = alpha; return 0; }
+
+int afe_batch_set_options(afe_batch *b, int stats_scope, int flags)
+{
+    return guarded([&] {
+        if (stats_scope < AFE_STATS_REFERENCE_BLOCK || stats_scope > AFE_STATS_CORPUS) throw Error("invalid stats scope");
+        if (b->d_tiles && ((stats_scope == AFE_STATS_CORPUS) != (b->scope == AFE_STATS_CORPUS)))
+            throw Error("set the statistics scope before afe_batch_plan");
+        b->scope = stats_scope; b->flags = flags;
+    });
+}
+
+int afe_batch_set_stream(afe_batch *b, void *cuda_stream)
+{
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return 0;
+}
+
+int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_utts, int64_t *total_frames)
+{
+    return guarded([&] {
+        const Derived &d = b->d;
+        if (n_utts < 1) throw Error("plan: no utterances");
+        DeviceGuard g(b->device);
+        b->free_plan();
+        // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
+        const char *env_tc = getenv("AFE_TILE_FRAMES");
+        int tc = env_tc ? atoi(env_tc) : 256;
+        tc = std::min(tc, (4096 / d.cols) / kSubBatch * kSubBatch);
+        tc = std::max(tc, kSubBatch * ((2 * d.D + 1 + kSubBatch - 1) / kSubBatch + 1));
+        b->tc_max = tc; b->nout_max = tc - 2 * d.D;
+        b->n_utts = n_utts;
+        b->sample_off.assign(off, off + n_utts);
+        b->pcm_extent = 0;
+        b->frame_off.assign(n_utts + 1, 0);
+        std::vector<Tile> tiles;
+        std::vector<int> tile_begin;
+        std::vector<double> counts;
+        const bool corpus = b->scope == AFE_STATS_CORPUS;
+        bool aligned = d.S % 8 == 0;
+        double corpus_count = 0;
+        for (int u = 0; u < n_utts; u++) {
+            const int64_t n = len[u];
+            if (n < 0 || n > 0x7fffffff || off[u] < 0) throw Error("plan: invalid utterance offset/length");
+            b->pcm_extent = std::max<int64_t>(b->pcm_extent, off[u] + n);
+            if (off[u] % 2) throw Error("plan: utterance offsets must be even (32-bit PCM word loads)");
+            if (off[u] % 8) aligned = false;
+            const int T = afe_estimated_window_count((int)n, d.W, d.S);
+            if (T <= 2 * d.D || T < 1) throw Error("Can't process data, window count is too small"); // segmentercpu.cpp:65-66
+            b->frame_off[u + 1] = b->frame_off[u] + T;
+            const int ntile = (T + b->nout_max - 1) / b->nout_max;
+            const int nout = (T + ntile - 1) / ntile;
+            if (!corpus) tile_begin.push_back((int)tiles.size());
+            for (int t0 = 0; t0 < T; t0 += nout) {
+                Tile tl;
+                tl.pcm_off = off[u]; tl.out_row0 = b->frame_off[u]; tl.T = T; tl.t0 = t0;
+                tl.nout = std::min(nout, T - t0); tl.group = corpus ? 0 : u;
+                tiles.push_back(tl);
+            }
+            const double cnt = !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
+            if (corpus) corpus_count += cnt; else counts.push_back(cnt);
+        }
+        if (corpus) { tile_begin.push_back(0); counts.push_back(corpus_count); }
+        tile_begin.push_back((int)tiles.size());
+        b->aligned = aligned;
+        b->n_tiles = (int)tiles.size();
+        b->n_groups = corpus ? 1 : n_utts;
+        b->L = d.N2 == 512 ? fused_smem_layout<512>(d.S, d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2)
+                           : fused_smem_layout<256>(d.S, d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2);
+        if (b->L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
+        AFE_CUDA(cudaMalloc(&b->d_tiles, sizeof(Tile) * tiles.size()));
+        AFE_CUDA(cudaMemcpy(b->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));
+        if (d.p.norm != AFE_NORM_NONE) {
+            const size_t w = d.width;
+            AFE_CUDA(cudaMalloc(&b->d_tile_begin, sizeof(int) * tile_begin.size()));
+            AFE_CUDA(cudaMemcpy(b->d_tile_begin, tile_begin.data(), sizeof(int) * tile_begin.size(), cudaMemcpyHostToDevice));
+            AFE_CUDA(cudaMalloc(&b->d_counts, sizeof(double) * counts.size()));
+            AFE_CUDA(cudaMemcpy(b->d_counts, counts.data(), sizeof(double) * counts.size(), cudaMemcpyHostToDevice));
+            AFE_CUDA(cudaMalloc(&b->d_partials, sizeof(double) * 4 * w * tiles.size()));
+            AFE_CUDA(cudaMalloc(&b->d_stats, sizeof(double) * (4 * w + 1) * b->n_groups));
+            AFE_CUDA(cudaMalloc(&b->d_mean, sizeof(float) * w * b->n_groups));
+            AFE_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * w * b->n_groups));
+        }
+        if (total_frames) *total_frames = b->frame_off[n_utts];
+    });
+}
+
+int afe_batch_frame_offsets(const afe_batch *b, int64_t *fo)
+{
+    memcpy(fo, b->frame_off.data(), sizeof(int64_t) * b->frame_off.size());
+    return 0;
+}
+int afe_batch_num_tiles(const afe_batch *b) { return b->n_tiles; }
+int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
+
+int afe_batch_extract_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
+{
+    return guarded([&] { DeviceGuard g(b->device); run_extract(b, d_pcm, d_out); });
+}
+
+int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
+            throw Error("corpus statistics need the two-pass sequence: extract_device, corpus_stats, allreduce, normalize_device");
+        run_extract(b, d_pcm, d_out);
+        if (b->d.p.norm != AFE_NORM_NONE) { run_reduce(b); run_normalize(b, d_out); }
+    });
+}
+
+int afe_batch_corpus_stats(afe_batch *b, double **d_stats, int *stats_len)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (b->d.p.norm == AFE_NORM_NONE) throw Error("corpus_stats: norm is NONE");
+        run_reduce(b);
+        if (d_stats) *d_stats = b->d_stats;
+        if (stats_len) *stats_len = (4 * b->d.width + 1) * b->n_groups;
+    });
+}
+
+int afe_normalizer_allreduce(afe_batch *b, void *comm)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (b->scope != AFE_STATS_CORPUS) throw Error("allreduce: statistics scope is not CORPUS");
+        const int w = b->d.width;
+        // one fused group: sums + count (ncclSum), minima (ncclMin), maxima (ncclMax) — 4w+1 doubles, latency bound
+        nccl_allreduce_stats(comm, b->d_stats, 2 * w + 1, b->d_stats + 2 * w + 1, w, b->d_stats + 3 * w + 1, w, b->stream);
+    });
+}
+
+int afe_batch_set_corpus_stats(afe_batch *b, const double *h_stats, int stats_len)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (stats_len != (4 * b->d.width + 1) * b->n_groups) throw Error("set_corpus_stats: wrong length");
+        AFE_CUDA(cudaMemcpyAsync(b->d_stats, h_stats, sizeof(double) * stats_len, cudaMemcpyHostToDevice, b->stream));
+        AFE_CUDA(cudaStreamSynchronize(b->stream));
+    });
+}
+
+int afe_batch_normalize_device(afe_batch *b, float *d_out)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (b->d.p.norm == AFE_NORM_NONE) return;
+        run_normalize(b, d_out);
+    });
+}
+
+int afe_batch_synchronize(afe_batch *b)
+{
+    return guarded([&] { DeviceGuard g(b->device); AFE_CUDA(cudaStreamSynchronize(b->stream)); });
+}
+
+// End-to-end with host buffers. h_pcm should be pinned for full PCIe speed (works with pageable memory too).
+int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
+{
+    return guarded([&] {
+        DeviceGuard g(b->device);
+        if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
+        const size_t n_samples = (size_t)b->pcm_extent;
+        const size_t pcm_bytes = n_samples * 2 + 32, out_bytes = (size_t)b->frame_off.back() * b->d.width * 4;
+        if (pcm_bytes > b->pcm_stage_bytes) {
+            if (b->d_pcm_stage) cudaFree(b->d_pcm_stage);
+            AFE_CUDA(cudaMalloc(&b->d_pcm_stage, pcm_bytes));
+            b->pcm_stage_bytes = pcm_bytes;
+        }
+        if (out_bytes > b->out_stage_bytes) {
+            if (b->d_out_stage) cudaFree(b->d_out_stage);
+            AFE_CUDA(cudaMalloc(&b->d_out_stage, out_bytes));
+            b->out_stage_bytes = out_bytes;
+        }
+        AFE_CUDA(cudaMemcpyAsync(b->d_pcm_stage, h_pcm, n_samples * 2, cudaMemcpyHostToDevice, b->stream));
+        if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
+            throw Error("run_host: corpus statistics need the two-pass device sequence");
+        run_extract(b, b->d_pcm_stage, b->d_out_stage);
+        if (b->d.p.norm != AFE_NORM_NONE) { run_reduce(b); run_normalize(b, b->d_out_stage); }
+        AFE_CUDA(cudaMemcpyAsync(h_out, b->d_out_stage, out_bytes, cudaMemcpyDeviceToHost, b->stream));
+        AFE_CUDA(cudaStreamSynchronize(b->stream));
+    });
+}
+
+} // extern "C"

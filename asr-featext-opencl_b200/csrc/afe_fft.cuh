@@ -1,0 +1,205 @@
+// In-register batched real FFT (256/512 point) + magnitude, replacing clfft.cpp / AppleFFT and mfcc.cl:kernelTranspose.
+//
+// An N2-point real frame is transformed as an M = N2/2 point complex FFT of z[n] = x[2n] + i*x[2n+1] (one 32-bit
+// shared-memory word holds both int16 samples), M = 16*R:
+//   R lanes cooperate on one frame (R = 16 for N2 = 512, R = 8 for N2 = 256), so a warp transforms 32/R frames at once.
+//   stage A   lane n2 holds z[R*n1 + n2], n1 = 0..15, and runs a radix-16 butterfly (4x4) entirely in registers
+//   twiddle   * exp(-2 pi i n2 k1 / M) from per-lane registers
+//   exchange  one trip through a padded shared-memory tile S[k1][n2] (the only data exchange of the transform)
+//   stage B   R-point FFT over n2 (radix-16, or two radix-8) in registers -> Z[k1 + 16 k2]
+//   split     X[k], X[M-k] from Z[k], Z[M-k] (second trip through the same tile), |X| * 0.5/N2 -> magnitude row
+// The index maps are modelled and checked against numpy.fft.rfft in tools/fft_model.py / tests/test_host_logic.py.
+// Reference semantics: fftwf r2c unnormalised (mfcccpu.cpp:114,189), v = sqrt(re^2+im^2)/N2 (mfcccpu.cpp:203).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace afe {
+namespace dev {
+
+constexpr float kC1 = 0.92387953251128674f; // cos(pi/8)
+constexpr float kS1 = 0.38268343236508977f; // sin(pi/8)
+constexpr float kR2 = 0.70710678118654752f; // sqrt(1/2)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// forward 4-point DFT, natural order in and out
+__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+    a0 = cadd(s02, s13);
+    a2 = csub(s02, s13);
+    a1 = make_float2(d02.x + d13.y, d02.y - d13.x); // d02 - i*d13
+    a3 = make_float2(d02.x - d13.y, d02.y + d13.x); // d02 + i*d13
+}
+
+// (x+iy) * exp(-i pi/4), * (-i), * exp(-3 i pi/4)
+__device__ __forceinline__ float2 mul_w8_1(float2 v) { return make_float2(kR2 * (v.x + v.y), kR2 * (v.y - v.x)); }
+__device__ __forceinline__ float2 mul_mi(float2 v) { return make_float2(v.y, -v.x); }
+__device__ __forceinline__ float2 mul_w8_3(float2 v) { return make_float2(kR2 * (v.y - v.x), -kR2 * (v.x + v.y)); }
+
+// forward 16-point DFT in registers. Input natural order; output X[k] lands in slot 4*(k%4) + k/4.
+__device__ __forceinline__ void fft16(float2 (&x)[16])
+{
+#pragma unroll
+    for (int b = 0; b < 4; b++) fft4(x[b], x[4 + b], x[8 + b], x[12 + b]);
+    // slot 4c+b *= W16^(b*c)
+    x[5] = cmul(x[5], make_float2(kC1, -kS1));   // W^1
+    x[6] = mul_w8_1(x[6]);                       // W^2
+    x[7] = cmul(x[7], make_float2(kS1, -kC1));   // W^3
+    x[9] = mul_w8_1(x[9]);                       // W^2
+    x[10] = mul_mi(x[10]);                       // W^4
+    x[11] = mul_w8_3(x[11]);                     // W^6
+    x[13] = cmul(x[13], make_float2(kS1, -kC1)); // W^3
+    x[14] = mul_w8_3(x[14]);                     // W^6
+    x[15] = cmul(x[15], make_float2(-kC1, kS1)); // W^9
+#pragma unroll
+    for (int c = 0; c < 4; c++) fft4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+__host__ __device__ constexpr int pos16(int k) { return 4 * (k % 4) + k / 4; }
+
+// forward 8-point DFT on x[o..o+7]. Output X[k] lands in slot o + 2*(k%4) + k/4.
+template <int O> __device__ __forceinline__ void fft8(float2 (&x)[16])
+{
+    fft4(x[O + 0], x[O + 2], x[O + 4], x[O + 6]);
+    fft4(x[O + 1], x[O + 3], x[O + 5], x[O + 7]);
+    x[O + 3] = mul_w8_1(x[O + 3]);
+    x[O + 5] = mul_mi(x[O + 5]);
+    x[O + 7] = mul_w8_3(x[O + 7]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float2 a = x[O + 2 * c], b = x[O + 2 * c + 1];
+        x[O + 2 * c] = cadd(a, b);
+        x[O + 2 * c + 1] = csub(a, b);
+    }
+}
+__host__ __device__ constexpr int pos8(int k) { return 2 * (k % 4) + k / 4; }
+
+template <int N2> struct FftCfg {
+    static_assert(N2 == 512 || N2 == 256, "in-register FFT supports 256 and 512 points");
+    static constexpr int M = N2 / 2;         // complex length
+    static constexpr int R = M / 16;         // lanes per frame
+    static constexpr int FPW = 32 / R;       // frames per warp
+    static constexpr int RS = R + 1;         // padded row stride of the exchange tile (float2 units)
+    static constexpr int SCR = 16 * RS + (R == 8 ? 1 : 0); // per-frame scratch (float2 units), >= M
+    static constexpr int BINS = M + 1;
+};
+
+// per-lane constants, loaded once per CTA
+template <int N2> struct LaneConsts {
+    float2 win[16]; // (w[2n], w[2n+1]) for n = R*n1 + lane
+    float2 twa[16]; // exp(-2 pi i lane*k1 / M)
+    float2 twp[8];  // exp(-2 pi i (lane + R*m) / N2)
+};
+
+template <int N2>
+__device__ __forceinline__ void load_lane_consts(LaneConsts<N2> &lc, const float2 *__restrict__ window2,
+                                                 const float2 *__restrict__ tw_a, const float2 *__restrict__ tw_p, int lf)
+{
+    using C = FftCfg<N2>;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) lc.win[n1] = window2[C::R * n1 + lf];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) lc.twa[k1] = tw_a[lf * 16 + k1];
+#pragma unroll
+    for (int m = 0; m < 8; m++) lc.twp[m] = tw_p[lf + C::R * m];
+}
+
+template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
+{
+    if (FAST) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    return sqrtf(x);
+}
+
+// One frame per R-lane group; ALL 32 lanes of the warp must call (uses __syncwarp).
+//   words    : the frame's PCM as 32-bit words (2 int16 each), readable for N2/2 words (values beyond W are multiplied by 0)
+//   nz       : number of leading n1 slots that can be non-zero = ceil(W / (2R)); others are skipped
+//   scratch  : this frame's exchange tile, FftCfg::SCR float2
+//   mag_out  : BINS floats, or nullptr for a padding frame (computed but not stored)
+template <int N2, bool FAST>
+__device__ __forceinline__ void fft_frame_mag(const uint32_t *words, int nz, const LaneConsts<N2> &lc, float2 *scratch,
+                                              float *mag_out, int lf)
+{
+    using C = FftCfg<N2>;
+    constexpr int M = C::M, R = C::R, RS = C::RS;
+    float2 x[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; n1++) {
+        if (n1 < nz) {
+            const uint32_t w = words[R * n1 + lf];
+            const float lo = (float)(int)(short)(w & 0xffffu);
+            const float hi = (float)((int)w >> 16);
+            x[n1] = make_float2(lo * lc.win[n1].x, hi * lc.win[n1].y);
+        } else
+            x[n1] = make_float2(0.f, 0.f);
+    }
+    fft16(x);
+    // twiddle + exchange: S[k1][n2]
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) {
+        float2 v = x[pos16(k1)];
+        if (k1 > 0) v = cmul(v, lc.twa[k1]);
+        scratch[k1 * RS + lf] = v;
+    }
+    __syncwarp();
+    if (R == 16) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; n2++) x[n2] = scratch[lf * RS + n2];
+        fft16(x);
+    } else {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) {
+            x[n2] = scratch[lf * RS + n2];
+            x[8 + n2] = scratch[(lf + 8) * RS + n2];
+        }
+        fft8<0>(x);
+        fft8<8>(x);
+    }
+    __syncwarp();
+    // Z[k] in natural order for the real split
+    if (R == 16) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) scratch[lf + 16 * k2] = x[pos16(k2)];
+    } else {
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            scratch[lf + 16 * k2] = x[pos8(k2)];
+            scratch[lf + 8 + 16 * k2] = x[8 + pos8(k2)];
+        }
+    }
+    __syncwarp();
+    const float scale = 0.5f / (float)N2; // |2X| * 0.5/N2 == |X|/N2 exactly (powers of two)
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int k = lf + R * m;
+        const float2 a = scratch[k];
+        const float2 b = scratch[(M - k) & (M - 1)];
+        const float2 w = lc.twp[m];
+        const float sr = a.x + b.x, si = a.y - b.y; // a + conj(b)
+        const float dr = a.x - b.x, di = a.y + b.y; // a - conj(b)
+        const float pr = dr * w.x - di * w.y, pi = dr * w.y + di * w.x;
+        const float x1r = sr + pi, x1i = si - pr;   // 2 X[k]
+        const float x2r = sr - pi, x2i = si + pr;   // 2 conj(X[M-k])
+        if (mag_out) {
+            mag_out[k] = mag_sqrt<FAST>(x1r * x1r + x1i * x1i) * scale;
+            mag_out[M - k] = mag_sqrt<FAST>(x2r * x2r + x2i * x2i) * scale;
+        }
+    }
+    if (lf == 0 && mag_out) {
+        const float2 a = scratch[M / 2]; // X[M/2] = conj(Z[M/2])
+        mag_out[M / 2] = mag_sqrt<FAST>(a.x * a.x + a.y * a.y) * (1.0f / (float)N2);
+    }
+    __syncwarp();
+}
+
+} // namespace dev
+} // namespace afe

@@ -1,0 +1,357 @@
+"""GPU tier (`-m gpu`): the CUDA path, called through the C ABI (ctypes), against the pinned CPU oracle on the same
+inputs. Tolerances are stated in tests/common.py:tolerances. Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from common import afe, assert_close, run_batch, synth_utterances, to_afe_params
+from golden_io import load_golden, load_pcm
+
+pytestmark = pytest.mark.gpu
+
+BIG = 1 << 22
+
+
+def oracle_extract(oracle, p, utts, sample_limit):
+    return oracle.extract(p, utts, sample_limit=sample_limit)[0]
+
+
+# ---------------------------------------------------------------------------------------------- streaming object
+@pytest.mark.parametrize("case", sorted(load_golden().keys()))
+def test_stream_object_matches_golden_and_oracle(oracle, case):
+    """MfccCuda driven like the reference driver drives ParamBase, block sizes as in the golden case."""
+    g = load_golden()[case]
+    p, pcm = g["params"], load_pcm()[g["utt"]]
+    limit = g["sample_limit"] if g["sample_limit"] > 0 else len(pcm)
+    got = afe.extract_stream(to_afe_params(p, limit), pcm, alpha=p["alpha"])
+    assert got.shape == (g["frames"], g["width"])
+    assert_close(got[g["rows"]], g["feats"], p, case + " vs golden")
+    want = oracle_extract(oracle, p, [pcm], g["sample_limit"])[0]
+    assert_close(got, want, p, case + " vs oracle")
+
+
+def test_stream_fix_flush_statics_option(oracle):
+    """AFE_OPT_FIX_FLUSH_STATICS: single block + flush gives the streamed (intended) statics for the last D rows."""
+    pcm = load_pcm()["a1"]
+    p = ol.default_params(dyn="acc")
+    want = oracle_extract(oracle, p, [pcm], 0)[0]           # 2 set_input calls -> no Q1
+    got = afe.extract_stream(to_afe_params(p, BIG), pcm, fix_flush_statics=True)
+    assert_close(got, want, p, "fixed flush")
+    exact = afe.extract_stream(to_afe_params(p, BIG), pcm)  # default: reference-exact (Q1)
+    assert_close(exact, oracle_extract(oracle, p, [pcm], BIG)[0], p, "q1 exact")
+
+
+def test_stream_vtln_sweep_reuses_spectrum(oracle):
+    """set_alpha + repeated apply() after ONE set_input (ASR_OCL.cpp:236-243): the spectrum must persist."""
+    pcm = load_pcm()["sample1"]
+    p = ol.default_params(dyn="acc", norm="cmn")
+    m = afe.MfccCuda(to_afe_params(p, BIG))
+    m.set_window(afe.make_window(400))
+    ref = ol.RefMfcc(oracle, BIG, p)
+    ref.set_window(oracle.window(400))
+    n = m.get_input_buffer_size()
+    assert n == ref.get_input_buffer_size()
+    wc = m.set_input(pcm[:n])
+    assert wc == ref.set_input(pcm[:n])
+    for alpha in (0.9, 1.0, 1.1):
+        m.set_alpha(alpha); ref.set_alpha(alpha)
+        m.apply(); ref.apply()
+        assert_close(m.get_output_data(wc), ref.get_output_data(wc), p, f"alpha={alpha}")
+    m.close(); ref.close()
+
+
+def test_stream_error_behaviour():
+    p = afe.make_params(input_buffer_size=16000, dyn=2)
+    m = afe.MfccCuda(p)
+    m.set_window(afe.make_window(400))
+    assert m.get_input_buffer_size() == 98 * 160 + 240                    # parambase.cpp:12-13
+    with pytest.raises(afe.AfeError, match="buffer is too small"):       # mfcccpu.cpp:338-339
+        m.set_input(np.zeros(m.get_input_buffer_size() + 1, np.int16))
+    with pytest.raises(afe.AfeError, match="window count is too small"):  # segmentercpu.cpp:65-66
+        m.set_input(np.zeros(400 + 160 * 5, np.int16))
+    m.reset()
+    assert m.set_input(np.zeros(m.get_input_buffer_size(), np.int16)) == 98 - 6
+    m.apply()
+    with pytest.raises(afe.AfeError, match="Window count too high"):      # mfcccpu.cpp:429-430
+        m.get_output_data(10_000)
+    assert m.flush() == 6
+    assert m.flush() == 0                                                 # idempotent (mfcccpu.cpp:350-352)
+    m.close()
+
+
+def test_stream_reset_makes_handle_reusable(oracle):
+    pcm = load_pcm()
+    p = ol.default_params(dyn="acc", norm="cmn")
+    m = afe.MfccCuda(to_afe_params(p, BIG))
+    m.set_window(afe.make_window(400))
+    for name in ("a1", "sample1"):
+        rows = []
+        wc = m.set_input(pcm[name]); m.apply(); rows.append(m.get_output_data(wc))
+        wc = m.flush(); m.apply(); rows.append(m.get_output_data(wc))
+        assert_close(np.concatenate(rows), oracle_extract(oracle, p, [pcm[name]], BIG)[0], p, name)
+        m.reset()
+    m.close()
+
+
+def test_stream_generic_fft_sizes(oracle):
+    """window sizes whose ceil2 is neither 256 nor 512 take the generic shared-memory FFT kernel."""
+    pcm = load_pcm()["sample1"]
+    for W, S in ((100, 40), (640, 160), (1024, 256)):
+        p = ol.default_params(window_size=W, shift=S, dyn="acc")
+        got = afe.extract_stream(to_afe_params(p, BIG), pcm, window=oracle.window(W))
+        want = oracle_extract(oracle, p, [pcm], BIG)[0]
+        assert_close(got, want, p, f"W={W}")
+
+
+# ---------------------------------------------------------------------------------------------- stage objects
+def test_segmenter_cuda_bit_exact_and_state(oracle):
+    pcm = load_pcm()["a1"]
+    W, S, D, limit = 400, 160, 6, 120
+    seg = afe.SegmenterCuda(W, S, limit, D)
+    seg.set_window(afe.make_window(W))
+    ref = oracle.segmenter_create(W, S, limit, D)
+    win = oracle.window(W)
+    oracle.segmenter_set_window(ref, win.ctypes.data_as(C.POINTER(C.c_float)))
+    buf = np.zeros((limit, 512), np.float32)
+    pos = 0
+    for n in (16000, 16000, 7000, 16000):
+        blk = np.ascontiguousarray(pcm[pos:pos + n]); pos += n
+        wc, nd = seg.set_input(blk)
+        rwc, rnd = C.c_int(0), C.c_int(0)
+        buf[:] = 0
+        assert oracle.segmenter_set_input(ref, blk.ctypes.data_as(C.POINTER(C.c_short)), buf.ctypes.data_as(C.POINTER(C.c_float)),
+                                          n, C.byref(rwc), C.byref(rnd)) == 0
+        assert (wc, nd) == (rwc.value, rnd.value)
+        assert seg.get_remaining_samples() == oracle.segmenter_remaining_samples(ref)
+        assert seg.get_samples() == oracle.segmenter_samples(ref)
+        assert seg.was_flushed() == bool(oracle.segmenter_was_flushed(ref))
+        np.testing.assert_array_equal(seg.frames(nd), buf[:nd])          # one fp32 multiply per sample: bit-exact
+    wc, nd = seg.flush()
+    rwc, rnd = C.c_int(0), C.c_int(0)
+    buf[:] = 0
+    oracle.segmenter_flush(ref, buf.ctypes.data_as(C.POINTER(C.c_float)), C.byref(rwc), C.byref(rnd))
+    assert (wc, nd) == (rwc.value, rnd.value) and seg.is_flushed()
+    np.testing.assert_array_equal(seg.frames(nd), buf[:nd])
+    oracle.segmenter_destroy(ref)
+    seg.close()
+
+
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_delta_cuda_bit_exact(oracle, L):
+    rng = np.random.default_rng(L)
+    rows, dim = 257, 13
+    x = rng.standard_normal((rows + 2 * L, dim)).astype(np.float32) * 10
+    want = np.zeros((rows, dim), np.float32)
+    fp = C.POINTER(C.c_float)
+    oracle.delta_apply(x.ctypes.data_as(fp), want.ctypes.data_as(fp), dim, rows, L)
+    d = afe.DeltaCuda(dim, rows, L)
+    np.testing.assert_array_equal(d.apply(x, rows), want)                # unfused mul/add/div like the CPU: bit-exact
+    d.close()
+
+
+@pytest.mark.parametrize("norm", ["cmn", "cvn", "minmax"])
+def test_normalizer_cuda(oracle, norm):
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((1000, 39)) * 4 + 11).astype(np.float32)
+    want = x.copy()
+    h = oracle.normalizer_create(ol.NORM[norm], 39)
+    oracle.normalizer_normalize(h, want.ctypes.data_as(C.POINTER(C.c_float)), 1000, 0)
+    n = afe.NormalizerCuda(ol.NORM[norm], 39)
+    got = n.normalize(x)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)             # double stats, summation order differs
+    tail = x[:9].copy()
+    oracle.normalizer_normalize(h, tail.ctypes.data_as(C.POINTER(C.c_float)), 9, 1)
+    np.testing.assert_allclose(n.normalize(x[:9], use_last_stats=True), tail, rtol=0, atol=2e-6)
+    oracle.normalizer_destroy(h)
+    n.close()
+
+
+# ---------------------------------------------------------------------------------------------- fused batch path
+SOUNDFILES = ["a0001", "a1", "a2", "a3", "a4", "a5"]
+
+
+@pytest.mark.parametrize("flags", [0, afe.BATCH_NO_TMA], ids=["tma", "plain-loads"])
+def test_batch_config2_soundfiles_q1_exact(oracle, flags):
+    """BASELINE config 2: a0001 + a1..a5, 23 mel, 12+c0, delta+delta-delta, per-utterance CMN, one block per
+    utterance. AFE_BATCH_Q1_EXACT == the reference driver with its default sample_limit (single set_input + flush)."""
+    pcm = load_pcm()
+    p = ol.default_params(norm="cmn", dyn="acc")
+    utts = [pcm[n] for n in SOUNDFILES]
+    got = run_batch(p, utts, flags=afe.BATCH_Q1_EXACT | flags)
+    want = oracle_extract(oracle, p, utts, BIG)
+    assert [len(g) for g in got] == [711, 504, 1011, 1517, 2023, 2529]
+    for n, g, w in zip(SOUNDFILES, got, want):
+        assert_close(g, w, p, n)
+    G = load_golden()
+    for n in SOUNDFILES:
+        gold = G[f"c2_{n}_single"]
+        assert_close(got[SOUNDFILES.index(n)][gold["rows"]], gold["feats"], p, n + " golden")
+
+
+def test_batch_config2_intended_semantics(oracle):
+    """Without the Q1 flag the last D rows carry their own statics == the reference fed in >= 2 blocks."""
+    pcm = load_pcm()
+    p = ol.default_params(norm="cmn", dyn="acc")
+    # a0001 and a2 are exactly frame aligned, so the reference would take them in ONE set_input even with
+    # sample_limit = N (Q1 again); three trailing zero samples force the second, frame-less block without adding a frame
+    utts = [np.concatenate([pcm[n], np.zeros(3, np.int16)]) for n in SOUNDFILES]
+    got = run_batch(p, utts)
+    want = oracle_extract(oracle, p, utts, 0)
+    for n, g, w in zip(SOUNDFILES, got, want):
+        assert_close(g, w, p, n)
+
+
+@pytest.mark.parametrize("case", ["c1_sample1", "c1_sample1_acc", "c3_a1_40mel", "c3_a1_40mel_nonorm", "v_a1_cvn",
+                                  "v_a1_minmax", "v_a1_delta_only", "v_a1_l1_2_l2_1", "v_a1_norm_before_dyn",
+                                  "v_a1_fbank", "v_a1_nolifter_noc0", "v_a1_alpha090", "v_a1_alpha112", "c5_a1_8k"])
+def test_batch_variants_match_golden(oracle, case):
+    g = load_golden()[case]
+    p, pcm = g["params"], load_pcm()[g["utt"]]
+    got = run_batch(p, [pcm], flags=afe.BATCH_Q1_EXACT)[0]
+    assert_close(got[g["rows"]], g["feats"], p, case + " vs golden")
+    assert_close(got, oracle_extract(oracle, p, [pcm], BIG)[0], p, case + " vs oracle")
+
+
+def test_batch_config3_synthetic_subset(oracle):
+    """BASELINE config 3 on a 48-utterance subset: synthetic 16 kHz, 10 s, 40 mel, 13 MFCC + d + dd, CMN."""
+    p = ol.default_params(num_banks=40, norm="cmn", dyn="acc")
+    utts = synth_utterances(48, 160000)
+    got = run_batch(p, utts, flags=afe.BATCH_Q1_EXACT)
+    want = oracle_extract(oracle, p, utts, BIG)
+    worst = (0.0, 0.0)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == (998, 39)
+        e = assert_close(g, w, p, f"utt {i}")
+        worst = max(worst, e)
+    print("config3 subset worst (static, delta) abs err:", worst)
+
+
+def test_batch_fast_math_within_tolerance(oracle):
+    p = ol.default_params(num_banks=40, norm="cmn", dyn="acc")
+    utts = synth_utterances(8, 160000, seed=7) + [load_pcm()["a1"]]
+    got = run_batch(p, utts, flags=afe.BATCH_Q1_EXACT | afe.BATCH_FAST_MATH)
+    want = oracle_extract(oracle, p, utts, BIG)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_close(g, w, p, f"fast utt {i}")
+
+
+def test_batch_config5_telephony_long_stream(oracle):
+    """BASELINE config 5 shape (8 kHz, 256-pt FFT, 20 mel, fused deltas) on a 60 s stream: many tiles with halos."""
+    p = ol.default_params(window_size=200, shift=80, num_banks=20, sample_rate=8000.0, high_freq=4000.0, dyn="acc")
+    x = synth_utterances(1, 480000, seed=5, sr=8000.0)[0]
+    got = run_batch(p, [x], flags=afe.BATCH_Q1_EXACT)[0]
+    want = oracle_extract(oracle, p, [x], BIG)[0]
+    assert got.shape == (5998, 39)
+    assert_close(got, want, p, "8k stream")
+    pc = dict(p, norm=ol.NORM["cmn"])
+    assert_close(run_batch(pc, [x], flags=afe.BATCH_Q1_EXACT)[0], oracle_extract(oracle, pc, [x], BIG)[0], pc, "8k cmn")
+
+
+def test_batch_ragged_and_edge_lengths(oracle):
+    """Ragged batch incl. the shortest legal utterance (T = 2D+1), a tile-boundary length and an odd sample count."""
+    p = ol.default_params(norm="cmn", dyn="acc")
+    D = 6
+    # (+k samples: not frame aligned, so the oracle with sample_limit = N needs a second set_input -> no Q1)
+    lens = [240 + 160 * (2 * D + 1) + 5, 240 + 160 * 244 + 1, 240 + 160 * 245 + 77, 240 + 160 * 489 + 3, 50001,
+            240 + 160 * 32 + 8]
+    utts = [synth_utterances(1, n, seed=n)[0] for n in lens]
+    got = run_batch(p, utts)
+    want = oracle_extract(oracle, p, utts, 0)
+    for n, g, w in zip(lens, got, want):
+        assert_close(g, w, p, f"len {n}")
+    with pytest.raises(afe.AfeError, match="window count is too small"):
+        run_batch(p, [np.zeros(240 + 160 * 2 * D, np.int16)])
+
+
+def test_batch_is_deterministic_and_order_independent():
+    """Size-independent properties at a larger size: bitwise repeatable; rows of an utterance do not depend on its
+    neighbours or on the staging path (TMA bulk copy vs plain loads)."""
+    p = ol.default_params(num_banks=40, norm="cmn", dyn="acc")
+    utts = synth_utterances(96, 160000, seed=11, ragged=True)
+    a = run_batch(p, utts)
+    b = run_batch(p, utts)
+    c = run_batch(p, utts[::-1])[::-1]
+    d = run_batch(p, utts, flags=afe.BATCH_NO_TMA)
+    for i in range(len(utts)):
+        np.testing.assert_array_equal(a[i], b[i])
+        np.testing.assert_array_equal(a[i], c[i])
+        np.testing.assert_array_equal(a[i], d[i])
+
+
+def test_batch_linearity_property():
+    """Without log the path would be linear; with it, scaling the PCM by 2 shifts every log-mel by ln 2, i.e. adds
+    ln2 * sum_k M[k][j] to cepstrum j and leaves deltas unchanged (checked on c0: sqrt(2/nb)*nb*ln 2)."""
+    p = ol.default_params(num_banks=40, dyn="acc")
+    x = synth_utterances(4, 80000, seed=3)
+    half = [(u // 2 * 1).astype(np.int16) for u in x]
+    dbl = [(h * 2).astype(np.int16) for h in half]
+    a, b = run_batch(p, half), run_batch(p, dbl)
+    shift = np.sqrt(2.0 / 40) * 40 * np.log(2.0)
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(v[:, 12] - u[:, 12], shift, atol=2e-4)
+        np.testing.assert_allclose(v[:, 13:], u[:, 13:], atol=2e-4)
+
+
+def test_batch_equals_stream_object():
+    """The fused kernel and the staged streaming path are two implementations of the same arithmetic."""
+    pcm = load_pcm()["a3"]
+    p = ol.default_params(norm="cvn", dyn="acc")
+    a = run_batch(p, [pcm], flags=afe.BATCH_Q1_EXACT)[0]
+    b = afe.extract_stream(to_afe_params(p, BIG), pcm)
+    np.testing.assert_allclose(a, b, atol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------- corpus CMVN
+@pytest.mark.parametrize("norm", ["cmn", "cvn", "minmax"])
+def test_corpus_cmvn_two_shards_equal_one(norm):
+    """Corpus statistics: (a) one batch; (b) two 'ranks' over disjoint utterance shards whose statistics records are
+    merged as the NCCL all-reduce merges them (sum | min | max) — must agree, and match NumPy on the raw features."""
+    p = ol.default_params(num_banks=40, norm=norm, dyn="acc")
+    utts = synth_utterances(24, 48000, seed=21, ragged=True)
+    w = ol.width_of(p)
+
+    def two_pass(shard, merged=None):
+        ap = to_afe_params(p, BIG)
+        b = afe.BatchMfcc(ap, 0, stats_scope=afe.STATS_CORPUS)
+        pcm, offs, lens = afe.pack_utterances(shard)
+        total = b.plan(offs, lens)
+        d_pcm = afe.DeviceBuffer(pcm.nbytes + 64); d_pcm.upload(pcm)
+        d_out = afe.DeviceBuffer(total * w * 4)
+        b.extract_device(d_pcm.ptr.value, d_out.ptr.value)
+        ptr, n = b.corpus_stats()
+        b.synchronize()
+        stats = np.zeros(n, np.float64)
+        afe._check(afe.lib().afe_memcpy_d2h(0, stats.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), stats.nbytes))
+        raw = d_out.download((total, w), np.float32)
+        if merged is not None:
+            b.set_corpus_stats(merged)
+        b.normalize_device(d_out.ptr.value)
+        b.synchronize()
+        out = d_out.download((total, w), np.float32)
+        b.close(); d_pcm.free(); d_out.free()
+        return raw, stats, out
+
+    raw, stats, one = two_pass(utts)
+    ra, sa, _ = two_pass(utts[:10])
+    rb, sb, _ = two_pass(utts[10:])
+    merged = np.concatenate([sa[:2 * w + 1] + sb[:2 * w + 1], np.minimum(sa[2 * w + 1:3 * w + 1], sb[2 * w + 1:3 * w + 1]),
+                             np.maximum(sa[3 * w + 1:], sb[3 * w + 1:])])
+    np.testing.assert_allclose(merged[:2 * w + 1], stats[:2 * w + 1], rtol=1e-12)
+    np.testing.assert_array_equal(merged[2 * w + 1:], stats[2 * w + 1:])
+    _, _, oa = two_pass(utts[:10], merged)
+    _, _, ob = two_pass(utts[10:], merged)
+    np.testing.assert_allclose(np.concatenate([oa, ob]), one, atol=1e-6)
+    # NumPy restatement of normalizercpu.cpp:31-66 over the whole corpus
+    x = raw.astype(np.float64)
+    mu = x.mean(0)
+    if norm == "cmn":
+        want = x - mu
+    elif norm == "cvn":
+        want = (x - mu) * np.sqrt((len(x) - 1) / ((x * x).sum(0) - x.sum(0) ** 2 / len(x)))
+    else:
+        want = (x - mu) / np.maximum(np.abs(x.min(0) - mu), np.abs(x.max(0) - mu))
+    np.testing.assert_allclose(one, want, atol=2e-5 if norm != "cvn" else 1e-5)
+    mean, scale = afe.cmvn_finalize_host(ol.NORM[norm], w, stats)
+    np.testing.assert_allclose(mean, mu, atol=1e-5)
