@@ -241,26 +241,27 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused_mfcc(const FusedArgs
         float *orow = a.out + (tl.out_row0 + t0) * (long long)width + col;
         for (int r = r_off; r < nout; r += rpp) {
             const int t = t0 + r;
-            float val;
+            float val, sval; // sval: the value the statistics see
             if (strm == 0) {
-                const int ts = (a.q1 && t >= T - D) ? t - D : t;
-                val = s_cep[(ts - c0f) * cols + c];
+                // Q1 shifts only what is WRITTEN for the flushed rows; the reference takes its statistics on the
+                // first block's own statics (mfcccpu.cpp:274 / :383-384), i.e. always un-shifted
+                sval = s_cep[(t - c0f) * cols + c];
+                val = (a.q1 && t >= T - D) ? s_cep[(t - D - c0f) * cols + c] : sval;
             } else if (strm == 1) {
-                val = s_dhat[(r + l2) * cols + c];
+                val = sval = s_dhat[(r + l2) * cols + c];
             } else {
                 float num = 0.f;
                 for (int l = 1; l <= l2; l++)
                     num = __fadd_rn(num, __fmul_rn((float)l, __fsub_rn(s_dhat[(r + l2 + l) * cols + c],
                                                                       s_dhat[(r + l2 - l) * cols + c])));
-                val = __fdiv_rn(num, a.den2);
+                val = sval = __fdiv_rn(num, a.den2);
             }
             orow[(long long)r * width] = val;
-            if (t < n_stats) {
-                // statistics use the un-shifted static (t < T-D whenever q1 could shift), normalizercpu.cpp:31-66
-                sum += (double)val;
-                sumsq += (double)__fmul_rn(val, val);
-                mn = fminf(mn, val);
-                mx = fmaxf(mx, val);
+            if (t < n_stats) { // normalizercpu.cpp:31-66: double sums of float values / float products
+                sum += (double)sval;
+                sumsq += (double)__fmul_rn(sval, sval);
+                mn = fminf(mn, sval);
+                mx = fmaxf(mx, sval);
             }
         }
     }

@@ -182,7 +182,9 @@ def run_b200(args):
     p = params_dict()
     ap = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in p.items() if k != "alpha"})
     flags = afe.BATCH_Q1_EXACT | (afe.BATCH_FAST_MATH if args.fast_math else 0) | (afe.BATCH_NO_TMA if args.no_tma else 0)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     b = afe.BatchMfcc(ap, local, stats_scope=afe.STATS_REFERENCE_BLOCK, flags=flags)
     b.set_stream(stream.cuda_stream)
     assert b.plan(offs, lens) == frames
