@@ -48,18 +48,28 @@ void MelTables::release()
     if (d_dct) cudaFree(d_dct);
     if (d_window) cudaFree(d_window);
     if (d_window2) cudaFree(d_window2);
+    if (d_fidx) cudaFree(d_fidx);
+    if (d_wlist) cudaFree(d_wlist);
+    d_fidx = nullptr; d_wlist = nullptr; nwl = 0;
     d_edges = nullptr; d_pairs = nullptr; d_dct = nullptr; d_window = nullptr; d_window2 = nullptr;
     alpha_built = -1.f;
 }
 
 void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st)
 {
-    std::vector<int> edges; std::vector<float> filters, pairs, dct;
+    std::vector<int> edges, fidx; std::vector<float> filters, pairs, dct, wlist;
     build_filters(d, alpha, edges, filters);
     for (int i = 0; i + 1 < (int)edges.size(); i++)
         if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     build_mel_pairs(d, edges, filters, pairs);
+    build_filter_lists(d, edges, filters, fidx, wlist);
+    if (!t.d_fidx) AFE_CUDA(cudaMalloc(&t.d_fidx, sizeof(int) * fidx.size()));
+    if (t.d_wlist && (int)wlist.size() > t.nwl) { cudaFree(t.d_wlist); t.d_wlist = nullptr; }
+    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins)));
+    t.nwl = (int)wlist.size();
+    AFE_CUDA(cudaMemcpyAsync(t.d_fidx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaMemcpyAsync(t.d_wlist, wlist.data(), sizeof(float) * wlist.size(), cudaMemcpyHostToDevice, st));
     if (!t.d_edges) AFE_CUDA(cudaMalloc(&t.d_edges, sizeof(int) * (d.nb + 2)));
     if (!t.d_pairs) AFE_CUDA(cudaMalloc(&t.d_pairs, sizeof(float) * 2 * d.bins));
     // pageable source + stream-ordered copy: cudaMemcpyAsync from pageable memory stages synchronously, safe with locals
@@ -195,13 +205,20 @@ static void check_fused_support(const Derived &d)
     if (d.nb + 2 > 256) throw Error("fused batch path supports num_banks <= 254");
 }
 
-template <int N2> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+template <int N2> static FusedSmem layout_for(const afe_batch *b)
+{
+    const Derived &d = b->d;
+    // wlist never exceeds 2 entries per bin (each bin feeds a rising and a falling side)
+    return fused_smem_layout<N2>(d.S, d.nb, 2 * d.bins, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2);
+}
+
+template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
 {
     const Derived &d = b->d;
     FusedArgs a{};
     a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles;
     a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.edges = b->mel.d_edges; a.pairs = reinterpret_cast<const float2 *>(b->mel.d_pairs); a.dct = b->mel.d_dct;
+    a.fidx = b->mel.d_fidx; a.wlist = b->mel.d_wlist; a.nwl = b->mel.nwl; a.dct = b->mel.d_dct;
     a.partials = want_stats ? b->d_partials : nullptr;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
@@ -211,13 +228,14 @@ template <int N2> static void launch_fused(afe_batch *b, const int16_t *d_pcm, f
     else if (!d.p.norm_after_dyn) a.stats_rows_mode = 2;
     else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
     a.tc_max = b->tc_max;
-    a.nz = std::min(16, (d.W + 2 * dev::FftCfg<N2>::R - 1) / (2 * dev::FftCfg<N2>::R));
     float den1 = 0, den2 = 0;
     for (int l = 1; l <= d.l1; l++) den1 += l * l;   // float accumulation like deltacpu.cpp:26
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
-    a.den1 = 2 * den1; a.den2 = 2 * den2;
+    a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
+    a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
+    if (a.nwl > 2 * d.bins) throw Error("mel weight list exceeds its shared-memory budget");
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, true> : k_fused_mfcc<N2, false>;
+    auto kern = fast ? k_fused_mfcc<N2, NZ, true> : k_fused_mfcc<N2, NZ, false>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
     kern<<<b->n_tiles, kFusedThreads, b->L.total, b->stream>>>(a, b->L);
     AFE_CUDA(cudaGetLastError());
@@ -232,8 +250,10 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
     if (b->mel.alpha_built != b->alpha) upload_mel_tables(b->d, b->alpha, b->mel, b->stream);
     b->last_launches = 0;
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
-    if (b->d.N2 == 512) launch_fused<512>(b, d_pcm, d_out, want_stats);
-    else launch_fused<256>(b, d_pcm, d_out, want_stats);
+    const int R = b->d.M / 16;
+    const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
+    if (b->d.N2 == 512) pruned ? launch_fused<512, 13>(b, d_pcm, d_out, want_stats) : launch_fused<512, 16>(b, d_pcm, d_out, want_stats);
+    else pruned ? launch_fused<256, 13>(b, d_pcm, d_out, want_stats) : launch_fused<256, 16>(b, d_pcm, d_out, want_stats);
 }
 
 static void run_reduce(afe_batch *b)
@@ -328,9 +348,9 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->free_plan();
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
         const char *env_tc = getenv("AFE_TILE_FRAMES");
-        int tc = env_tc ? atoi(env_tc) : 256;
-        tc = std::min(tc, (4096 / d.cols) / kSubBatch * kSubBatch);
-        tc = std::max(tc, kSubBatch * ((2 * d.D + 1 + kSubBatch - 1) / kSubBatch + 1));
+        int tc = env_tc ? atoi(env_tc) : 264;
+        tc = std::min(tc, (4096 / d.cols) / kRound * kRound);
+        tc = std::max(tc, kRound * ((2 * d.D + 1 + kRound - 1) / kRound + 1));
         b->tc_max = tc; b->nout_max = tc - 2 * d.D;
         b->n_utts = n_utts;
         b->sample_off.assign(off, off + n_utts);
@@ -368,8 +388,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->aligned = aligned;
         b->n_tiles = (int)tiles.size();
         b->n_groups = corpus ? 1 : n_utts;
-        b->L = d.N2 == 512 ? fused_smem_layout<512>(d.S, d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2)
-                           : fused_smem_layout<256>(d.S, d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2);
+        b->L = d.N2 == 512 ? layout_for<512>(b) : layout_for<256>(b);
         if (b->L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
         AFE_CUDA(cudaMalloc(&b->d_tiles, sizeof(Tile) * tiles.size()));
         AFE_CUDA(cudaMemcpy(b->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));

@@ -90,24 +90,41 @@ template <int N2> struct FftCfg {
     static constexpr int BINS = M + 1;
 };
 
-// per-lane constants, loaded once per CTA
-template <int N2> struct LaneConsts {
-    float2 win[16]; // (w[2n], w[2n+1]) for n = R*n1 + lane
-    float2 twa[16]; // exp(-2 pi i lane*k1 / M)
-    float2 twp[8];  // exp(-2 pi i (lane + R*m) / N2)
-};
-
-template <int N2>
-__device__ __forceinline__ void load_lane_consts(LaneConsts<N2> &lc, const float2 *__restrict__ window2,
-                                                 const float2 *__restrict__ tw_a, const float2 *__restrict__ tw_p, int lf)
+// forward 16-point DFT whose inputs x[NZ..15] are known to be zero (zero-padded window tail): prunes the first
+// radix-4 layer. NZ >= 13 keeps x[0..12]; anything else falls back to the full butterfly.
+template <int NZ> __device__ __forceinline__ void fft16_in(float2 (&x)[16])
 {
-    using C = FftCfg<N2>;
+    if (NZ == 13) {
+        fft4(x[0], x[4], x[8], x[12]);
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) lc.win[n1] = window2[C::R * n1 + lf];
+        for (int b = 1; b < 4; b++) { // a3 == 0: s13 = d13 = a1
+            const float2 a0 = x[b], a1 = x[4 + b], a2 = x[8 + b];
+            const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+            x[b] = cadd(s02, a1);
+            x[8 + b] = csub(s02, a1);
+            x[4 + b] = make_float2(d02.x + a1.y, d02.y - a1.x);
+            x[12 + b] = make_float2(d02.x - a1.y, d02.y + a1.x);
+        }
+        x[5] = cmul(x[5], make_float2(kC1, -kS1));
+        x[6] = mul_w8_1(x[6]);
+        x[7] = cmul(x[7], make_float2(kS1, -kC1));
+        x[9] = mul_w8_1(x[9]);
+        x[10] = mul_mi(x[10]);
+        x[11] = mul_w8_3(x[11]);
+        x[13] = cmul(x[13], make_float2(kS1, -kC1));
+        x[14] = mul_w8_3(x[14]);
+        x[15] = cmul(x[15], make_float2(-kC1, kS1));
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) lc.twa[k1] = tw_a[lf * 16 + k1];
+        for (int c = 0; c < 4; c++) fft4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+    } else
+        fft16(x);
+}
+
+// twiddles of the stage A -> stage B exchange, per lane, kept in registers: exp(-2 pi i lane*k1 / M), k1 = 0..15
+template <int N2> __device__ __forceinline__ void load_twa(float2 (&twa)[16], const float2 *__restrict__ tw_a, int lf)
+{
 #pragma unroll
-    for (int m = 0; m < 8; m++) lc.twp[m] = tw_p[lf + C::R * m];
+    for (int k1 = 0; k1 < 16; k1++) twa[k1] = tw_a[lf * 16 + k1];
 }
 
 template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
@@ -120,34 +137,37 @@ template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
     return sqrtf(x);
 }
 
-// One frame per R-lane group; ALL 32 lanes of the warp must call (uses __syncwarp).
-//   words    : the frame's PCM as 32-bit words (2 int16 each), readable for N2/2 words (values beyond W are multiplied by 0)
-//   nz       : number of leading n1 slots that can be non-zero = ceil(W / (2R)); others are skipped
+// One frame per R-lane group; ALL 32 lanes of the warp must call (uses __syncwarp). Branch free.
+//   words    : the frame's PCM as 32-bit words (2 int16 each), readable for NZ*R words; samples beyond W meet a 0 window
+//   NZ       : leading n1 slots that can be non-zero (13 when W <= 26*R, else 16)
+//   win2     : (w[2n], w[2n+1]) for n < M, zero padded (shared memory)
+//   twp      : exp(-2 pi i k / N2), k < M/2 (shared memory)
 //   scratch  : this frame's exchange tile, FftCfg::SCR float2
-//   mag_out  : BINS floats, or nullptr for a padding frame (computed but not stored)
-template <int N2, bool FAST>
-__device__ __forceinline__ void fft_frame_mag(const uint32_t *words, int nz, const LaneConsts<N2> &lc, float2 *scratch,
-                                              float *mag_out, int lf)
+//   mag_out  : BINS floats (always written; padding frames point at a row nobody reads)
+template <int N2, int NZ, bool FAST>
+__device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const float2 *win2, const float2 *twp,
+                                              const float2 (&twa)[16], float2 *scratch, float *mag_out, int lf)
 {
     using C = FftCfg<N2>;
     constexpr int M = C::M, R = C::R, RS = C::RS;
     float2 x[16];
 #pragma unroll
     for (int n1 = 0; n1 < 16; n1++) {
-        if (n1 < nz) {
+        if (n1 < NZ) {
             const uint32_t w = words[R * n1 + lf];
+            const float2 wn = win2[R * n1 + lf];
             const float lo = (float)(int)(short)(w & 0xffffu);
             const float hi = (float)((int)w >> 16);
-            x[n1] = make_float2(lo * lc.win[n1].x, hi * lc.win[n1].y);
+            x[n1] = make_float2(lo * wn.x, hi * wn.y);
         } else
             x[n1] = make_float2(0.f, 0.f);
     }
-    fft16(x);
+    fft16_in<NZ>(x);
     // twiddle + exchange: S[k1][n2]
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
         float2 v = x[pos16(k1)];
-        if (k1 > 0) v = cmul(v, lc.twa[k1]);
+        if (k1 > 0) v = cmul(v, twa[k1]);
         scratch[k1 * RS + lf] = v;
     }
     __syncwarp();
@@ -165,7 +185,7 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, int nz, con
         fft8<8>(x);
     }
     __syncwarp();
-    // Z[k] in natural order for the real split
+    // Z[k] in natural order for the real split, with Z[M] := Z[0] so that the mirror index never wraps
     if (R == 16) {
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) scratch[lf + 16 * k2] = x[pos16(k2)];
@@ -176,25 +196,26 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, int nz, con
             scratch[lf + 8 + 16 * k2] = x[8 + pos8(k2)];
         }
     }
+    if (lf == 0) scratch[M] = x[0];
     __syncwarp();
     const float scale = 0.5f / (float)N2; // |2X| * 0.5/N2 == |X|/N2 exactly (powers of two)
+    const float2 *fwd = scratch + lf, *rev = scratch + (M - lf);
+    float *mf = mag_out + lf, *mr = mag_out + (M - lf);
+    const float2 *tw = twp + lf;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        const int k = lf + R * m;
-        const float2 a = scratch[k];
-        const float2 b = scratch[(M - k) & (M - 1)];
-        const float2 w = lc.twp[m];
+        const float2 a = fwd[R * m];
+        const float2 b = rev[-R * m];
+        const float2 w = tw[R * m];
         const float sr = a.x + b.x, si = a.y - b.y; // a + conj(b)
         const float dr = a.x - b.x, di = a.y + b.y; // a - conj(b)
         const float pr = dr * w.x - di * w.y, pi = dr * w.y + di * w.x;
         const float x1r = sr + pi, x1i = si - pr;   // 2 X[k]
         const float x2r = sr - pi, x2i = si + pr;   // 2 conj(X[M-k])
-        if (mag_out) {
-            mag_out[k] = mag_sqrt<FAST>(x1r * x1r + x1i * x1i) * scale;
-            mag_out[M - k] = mag_sqrt<FAST>(x2r * x2r + x2i * x2i) * scale;
-        }
+        mf[R * m] = mag_sqrt<FAST>(x1r * x1r + x1i * x1i) * scale;
+        mr[-R * m] = mag_sqrt<FAST>(x2r * x2r + x2i * x2i) * scale;
     }
-    if (lf == 0 && mag_out) {
+    if (lf == 0) {
         const float2 a = scratch[M / 2]; // X[M/2] = conj(Z[M/2])
         mag_out[M / 2] = mag_sqrt<FAST>(a.x * a.x + a.y * a.y) * (1.0f / (float)N2);
     }

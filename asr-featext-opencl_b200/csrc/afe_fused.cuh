@@ -1,13 +1,17 @@
-// K1: the fused hot-path kernel.  int16 PCM tile -> window -> real FFT -> |X|/N2 -> mel+log -> DCT -> delta/delta-delta
-// -> feature rows (+ per-tile column statistics), one HBM read of PCM and one HBM write of features per frame.
+// K1: the fused hot-path kernel.  int16 PCM -> window -> real FFT -> |X|/N2 -> mel+log -> DCT -> delta/delta-delta
+// -> feature rows (+ per-tile column statistics): one HBM read of PCM and one HBM write of features per frame.
 //
 // Work item = (utterance, tile of `nout` output frames). A CTA computes the cepstra of its tile plus a halo of
 // D = l1+l2 frames on each side (clamped at the utterance edges, where the reference replicates the edge frame,
-// mfcccpu.cpp:243-254) in sub-batches of 32 frames:
-//   stage 0  PCM of the sub-batch lands in shared memory by one cp.async.bulk (TMA) per sub-batch, double buffered
-//            (plain vector loads when the shard is not 16-byte aligned)
-//   phase 1  4 warps x (32/R frames) : in-register FFT + magnitude      (afe_fft.cuh)   -> mags[32][bins] (smem)
-//   phase 2  one thread per frame    : mel + log + DCT                   (afe_mel.cuh)   -> cep[tile][cols] (smem)
+// mfcccpu.cpp:243-254). Inside the CTA every WARP IS AUTONOMOUS: it owns rounds of 8 consecutive frames and runs
+//   stage 0  one cp.async.bulk (TMA, SASS UBLKCP) of the round's PCM into the warp's own staging buffer, completion on
+//            the warp's own mbarrier; the next round's copy is issued as soon as the FFTs of this round are done
+//   phase 1  8/FPW calls of the in-register FFT + magnitude (afe_fft.cuh)            -> warp-private mags[8][260]
+//   phase 2  mel + log + DCT with 4 lanes per frame, each lane owning the filters b = q (mod 4) (summation order per
+//            filter = the reference's ascending-bin order, mfcccpu.cpp:192-220)       -> cep[tile][cols] (CTA shared)
+// with only __syncwarp between the steps, so warps of the resident CTAs interleave freely and no warp ever waits
+// at a CTA barrier inside the loop (v1 lost 39 % of its issue slots there, profiles/r01_v1_k_fused_summary.txt).
+// One __syncthreads later:
 //   phase 3  delta on the extended axis -> smem, then rows [static | delta | delta-delta] are written coalesced;
 //            column sums / sums of squares (double) / min / max of the tile go to a per-tile partial record.
 // Replaces, for whole utterances: segmenter.cl, AppleFFT fft0, mfcc.cl kernelTranspose+kernelFilter, DCT.cl,
@@ -34,46 +38,57 @@ struct FusedArgs {
     float *out;
     const Tile *tiles;
     const float2 *window2, *tw_a, *tw_p;
-    const int *edges;
-    const float2 *pairs;
+    const int *fidx;     // [3][nb]: per filter first bin, number of bins, offset into wlist
+    const float *wlist;  // concatenated triangular weights, filter by filter
     const float *dct;
     double *partials;    // [ntiles][width][4] or nullptr
-    int W, S, nb, dct_len, cols, width, l1, l2, nstreams;
+    int W, S, nb, dct_len, cols, width, l1, l2, nstreams, nwl;
     int q1;              // reproduce the single-block flush quirk
     int use_tma;
     int stats_rows_mode; // 0: no stats, 1: rows < T-D, 2: all rows
     int tc_max;          // capacity (frames) of the cepstra tile
-    int nz;              // non-zero n1 slots of the window
-    float den1, den2;    // 2*sum(l^2)
+    float rden1, rden2;  // 1 / (2*sum(l^2))
 };
 
-constexpr int kFusedThreads = 128;
 constexpr int kFusedWarps = 4;
-constexpr int kSubBatch = 32;
+constexpr int kFusedThreads = 32 * kFusedWarps;
+constexpr int kRound = 8;       // frames per warp round
+constexpr int kMagStride = 260; // floats per magnitude row: = 4 (mod 32), so phase 2's 8 frames x 4 lanes hit 32 banks
 
 struct FusedSmem {
-    int off_mbar, off_edges, off_pairs, off_dct, off_pcm, pcm_bytes, off_scratch, off_mags, off_cep, off_red, total;
+    int off_mbar, off_win, off_twp, off_fidx, off_wlist, off_dct, off_warp, warp_bytes, w_pcm, w_scratch, w_mags,
+        pcm_bytes, off_red, off_cep, total;
 };
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-template <int N2> FusedSmem fused_smem_layout(int S, int nb, int dct_len, int cols, int tc_max, int nout_max, int l2)
+template <int N2>
+FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int tc_max, int nout_max, int l2)
 {
     using C = dev::FftCfg<N2>;
     FusedSmem L;
     int o = 0;
-    L.off_mbar = o; o += 16;
-    L.off_edges = o; o += align_up((nb + 2) * 4, 16);
-    L.off_pairs = o; o += align_up(C::BINS * 8, 16);
+    L.off_mbar = o; o += align_up(kFusedWarps * 8, 16); // one mbarrier per warp, never aliased
+    L.off_win = o; o += align_up(C::M * 8, 16);
+    L.off_twp = o; o += align_up(C::M / 2 * 8, 16);
+    L.off_fidx = o; o += align_up(3 * nb * 4, 16);
+    L.off_wlist = o; o += align_up(nwl * 4, 16);
     L.off_dct = o; o += align_up((dct_len > 0 ? nb * dct_len : 1) * 4, 16);
-    L.pcm_bytes = align_up(((kSubBatch - 1) * S + N2) * 2, 16) + 16;
-    L.off_pcm = o; o += 2 * L.pcm_bytes;
-    L.off_scratch = o; o += align_up(kFusedWarps * C::FPW * C::SCR * 8, 16);
-    const int mags = kSubBatch * C::BINS * 4;
-    const int dhat = (nout_max + 2 * l2) * cols * 4;
-    L.off_mags = o; o += align_up(mags > dhat ? mags : dhat, 16);
+    // per warp: [pcm | scratch | mags]
+    int w = 0;
+    L.pcm_bytes = align_up(((kRound - 1) * S + N2) * 2, 16) + 16;
+    L.w_pcm = w; w += L.pcm_bytes;
+    L.w_scratch = w; w += align_up(C::FPW * C::SCR * 8, 16);
+    L.w_mags = w; w += align_up(kRound * kMagStride * 4, 16);
+    L.warp_bytes = align_up(w, 128);
+    // phase 3 reuses the per-warp area: [delta rows | reduction scratch]
+    const int dhat = align_up((nout_max + 2 * l2) * cols * 4, 16);
+    const int phase3 = dhat + kFusedThreads * 4 * 8;
+    o = align_up(o, 128);
+    L.off_warp = o;
+    L.off_red = o + dhat;
+    o += align_up(kFusedWarps * L.warp_bytes > phase3 ? kFusedWarps * L.warp_bytes : phase3, 128);
     L.off_cep = o; o += align_up(tc_max * cols * 4, 16);
-    L.off_red = o; o += kFusedThreads * 4 * 8;
     L.total = o;
     return L;
 }
@@ -119,98 +134,136 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 } // namespace dev
 
-template <int N2, bool FAST>
-__global__ void __launch_bounds__(kFusedThreads, 2) k_fused_mfcc(const FusedArgs a, const FusedSmem L)
+template <int N2, int NZ, bool FAST>
+__global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs a, const FusedSmem L)
 {
     using C = dev::FftCfg<N2>;
-    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, BINS = C::BINS, SB = kSubBatch;
+    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, M = C::M, MS = kMagStride;
+    constexpr int ITERS = kRound / FPW; // FFT calls per round
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *s_mbar = reinterpret_cast<uint64_t *>(smem + L.off_mbar);
-    int *s_edges = reinterpret_cast<int *>(smem + L.off_edges);
-    float2 *s_pairs = reinterpret_cast<float2 *>(smem + L.off_pairs);
+    float2 *s_win = reinterpret_cast<float2 *>(smem + L.off_win);
+    float2 *s_twp = reinterpret_cast<float2 *>(smem + L.off_twp);
+    int *s_fstart = reinterpret_cast<int *>(smem + L.off_fidx);
+    int *s_flen = s_fstart + a.nb, *s_woff = s_flen + a.nb;
+    float *s_wlist = reinterpret_cast<float *>(smem + L.off_wlist);
     float *s_dct = reinterpret_cast<float *>(smem + L.off_dct);
-    unsigned char *s_pcm = smem + L.off_pcm;
-    float2 *s_scratch = reinterpret_cast<float2 *>(smem + L.off_scratch);
-    float *s_mags = reinterpret_cast<float *>(smem + L.off_mags);
-    float *s_dhat = s_mags; // aliased after the last sub-batch
     float *s_cep = reinterpret_cast<float *>(smem + L.off_cep);
-    double *s_red = reinterpret_cast<double *>(smem + L.off_red);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lf = lane % R, fw = lane / R;
+    unsigned char *wbase = smem + L.off_warp + warp * L.warp_bytes;
+    uint64_t *w_mbar = reinterpret_cast<uint64_t *>(smem + L.off_mbar) + warp;
+    unsigned char *w_pcm = wbase + L.w_pcm;
+    float2 *w_scratch = reinterpret_cast<float2 *>(wbase + L.w_scratch);
+    float *w_mags = reinterpret_cast<float *>(wbase + L.w_mags);
+
     const Tile tl = a.tiles[blockIdx.x];
     const int D = a.l1 + a.l2, cols = a.cols;
     const int c0f = max(0, tl.t0 - D), c1f = min(tl.T, tl.t0 + tl.nout + D);
     const int ncomp = c1f - c0f;
-    const int nsub = (ncomp + SB - 1) / SB;
-    const int16_t *upcm = a.pcm + tl.pcm_off;
+    const int nrounds = (ncomp + kRound - 1) / kRound;
+    const int16_t *upcm = a.pcm + tl.pcm_off + (long long)c0f * a.S;
 
-    for (int i = tid; i < a.nb + 2; i += kFusedThreads) s_edges[i] = a.edges[i];
-    for (int i = tid; i < BINS; i += kFusedThreads) s_pairs[i] = a.pairs[i];
+    auto round_bytes = [&](int r) {
+        return (uint32_t)((((min(kRound, ncomp - r * kRound) - 1) * a.S + a.W) * 2 + 15) & ~15);
+    };
+    // issue the first copy before anything else so that it overlaps the table loads
+    if (a.use_tma && lane == 0) {
+        dev::mbar_init(w_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (warp < nrounds) {
+            const uint32_t bytes = round_bytes(warp);
+            dev::mbar_expect_tx(w_mbar, bytes);
+            dev::tma_bulk_g2s(w_pcm, upcm + (long long)warp * kRound * a.S, bytes, w_mbar);
+        }
+    }
+    for (int i = tid; i < M; i += kFusedThreads) s_win[i] = a.window2[i];
+    for (int i = tid; i < M / 2; i += kFusedThreads) s_twp[i] = a.tw_p[i];
+    for (int i = tid; i < 3 * a.nb; i += kFusedThreads) s_fstart[i] = a.fidx[i];
+    for (int i = tid; i < a.nwl; i += kFusedThreads) s_wlist[i] = a.wlist[i];
     if (a.dct_len > 0)
         for (int i = tid; i < a.nb * a.dct_len; i += kFusedThreads) s_dct[i] = a.dct[i];
-    dev::LaneConsts<N2> lc;
-    dev::load_lane_consts<N2>(lc, a.window2, a.tw_a, a.tw_p, lf);
-
-    if (a.use_tma && tid == 0) {
-        dev::mbar_init(&s_mbar[0], 1);
-        dev::mbar_init(&s_mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    float2 twa[16];
+    dev::load_twa<N2>(twa, a.tw_a, lf);
     __syncthreads();
 
-    auto sub_samples = [&](int s) { return (min(SB, ncomp - s * SB) - 1) * a.S + a.W; };
-    auto issue_tma = [&](int s) { // one thread
-        const uint32_t bytes = (uint32_t)((sub_samples(s) * 2 + 15) & ~15);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        dev::mbar_expect_tx(&s_mbar[s & 1], bytes);
-        dev::tma_bulk_g2s(s_pcm + (s & 1) * L.pcm_bytes, upcm + (long long)(c0f + s * SB) * a.S, bytes, &s_mbar[s & 1]);
-    };
-    if (a.use_tma && tid == 0) {
-        issue_tma(0);
-        if (nsub > 1) issue_tma(1);
-    }
-
-    for (int s = 0; s < nsub; s++) {
-        const int nf = min(SB, ncomp - s * SB);
-        const unsigned char *pcm_buf;
+    const int f2 = lane >> 2, q = lane & 3; // phase 2: frame within the round, lane within the frame
+    uint32_t parity = 0;
+    for (int r = warp; r < nrounds; r += kFusedWarps) {
+        const int f0 = r * kRound;
         if (a.use_tma) {
-            pcm_buf = s_pcm + (s & 1) * L.pcm_bytes;
-            dev::mbar_wait(&s_mbar[s & 1], (uint32_t)((s >> 1) & 1));
+            dev::mbar_wait(w_mbar, parity);
+            parity ^= 1;
         } else {
-            // plain staging: 16-bit elements (any alignment); the aligned fast path is the TMA branch
-            pcm_buf = s_pcm;
-            const int16_t *src = upcm + (long long)(c0f + s * SB) * a.S;
-            int16_t *dst = reinterpret_cast<int16_t *>(s_pcm);
-            const int n = sub_samples(s);
+            // plain staging (any alignment): the round's samples, 32-bit words when the source allows
+            const int16_t *src = upcm + (long long)f0 * a.S;
+            const int n = (min(kRound, ncomp - f0) - 1) * a.S + a.W;
+            int16_t *dst = reinterpret_cast<int16_t *>(w_pcm);
             if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
                 const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
                 uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-                for (int i = tid; i < n / 2; i += kFusedThreads) d32[i] = __ldg(s32 + i);
-                if ((n & 1) && tid == 0) dst[n - 1] = src[n - 1];
+                for (int i = lane; i < n / 2; i += 32) d32[i] = __ldg(s32 + i);
+                if ((n & 1) && lane == 0) dst[n - 1] = src[n - 1];
             } else
-                for (int i = tid; i < n; i += kFusedThreads) dst[i] = src[i];
-            __syncthreads();
+                for (int i = lane; i < n; i += 32) dst[i] = src[i];
+            __syncwarp();
         }
-        // ---- phase 1: FFT + magnitude, FPW frames per warp iteration
-        for (int it = warp; it * FPW < nf; it += kFusedWarps) {
-            const int fl = it * FPW + fw;
-            const bool act = fl < nf;
-            const int flc = act ? fl : nf - 1;
-            const uint32_t *words = reinterpret_cast<const uint32_t *>(pcm_buf) + ((flc * a.S) >> 1);
-            dev::fft_frame_mag<N2, FAST>(words, a.nz, lc, s_scratch + (warp * FPW + fw) * SCR,
-                                         act ? s_mags + fl * BINS : nullptr, lf);
+        // ---- phase 1: FFT + magnitude. Call `it` transforms frames it + fw*ITERS of the round (rows 16 banks apart)
+#pragma unroll 1
+        for (int it = 0; it < ITERS; it++) {
+            const int fl = it + fw * ITERS;
+            const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
+            dev::fft_frame_mag<N2, NZ, true>(words, s_win, s_twp, twa, w_scratch + fw * SCR, w_mags + fl * MS, lf);
         }
-        __syncthreads();
-        if (a.use_tma && tid == 0 && s + 2 < nsub) issue_tma(s + 2);
-        // ---- phase 2: mel + log + DCT, one thread per frame
-        if (tid < nf)
-            dev::mel_dct_frame<16, FAST>(s_mags + tid * BINS, s_edges, s_pairs, s_dct, a.nb, a.dct_len,
-                                         s_cep + (s * SB + tid) * cols);
-        __syncthreads();
+        // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
+        if (a.use_tma && lane == 0 && r + kFusedWarps < nrounds) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = round_bytes(r + kFusedWarps);
+            dev::mbar_expect_tx(w_mbar, bytes);
+            dev::tma_bulk_g2s(w_pcm, upcm + (long long)(r + kFusedWarps) * kRound * a.S, bytes, w_mbar);
+        }
+        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+4, ... of frame f2
+        {
+            const float *mrow = w_mags + f2 * MS;
+            float cep[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) cep[c] = 0.f;
+            float *crow = s_cep + (f0 + f2) * cols;
+            const bool live = f0 + f2 < ncomp;
+            for (int b = q; b < a.nb; b += 4) {
+                const int n = s_flen[b];
+                const float *mv = mrow + s_fstart[b];
+                const float *wv = s_wlist + s_woff[b];
+                float acc = 0.f;
+                for (int i = 0; i < n; i++) acc = fmaf(wv[i], mv[i], acc);
+                const float e = dev::mel_log<FAST>(acc);
+                if (a.dct_len > 0) {
+                    const float *row = s_dct + b * a.dct_len;
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (c < a.dct_len) cep[c] = fmaf(e, row[c], cep[c]);
+                } else if (live)
+                    crow[b] = e;
+            }
+            if (a.dct_len > 0) {
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    if (c < a.dct_len) {
+                        float v = cep[c];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        if (live && (c & 3) == q) crow[c] = v;
+                    }
+                }
+            }
+        }
+        __syncwarp(); // mags are rewritten by the next round's phase 1
     }
+    __syncthreads();
 
     // ---- phase 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
+    float *s_dhat = reinterpret_cast<float *>(smem + L.off_warp);
+    double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;
     if (a.nstreams >= 2) {
         const int nd = nout + 2 * l2;
@@ -221,9 +274,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused_mfcc(const FusedArgs
             for (int l = 1; l <= l1; l++) {
                 const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
                 const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
-                num = __fadd_rn(num, __fmul_rn((float)l, __fsub_rn(hi, lo))); // deltacpu.cpp:25, unfused like the CPU
+                num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
             }
-            s_dhat[idx] = __fdiv_rn(num, a.den1);
+            s_dhat[idx] = num * a.rden1;
         }
         __syncthreads();
     }
@@ -251,10 +304,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused_mfcc(const FusedArgs
                 val = sval = s_dhat[(r + l2) * cols + c];
             } else {
                 float num = 0.f;
-                for (int l = 1; l <= l2; l++)
-                    num = __fadd_rn(num, __fmul_rn((float)l, __fsub_rn(s_dhat[(r + l2 + l) * cols + c],
-                                                                      s_dhat[(r + l2 - l) * cols + c])));
-                val = sval = __fdiv_rn(num, a.den2);
+                const float *dc = s_dhat + (r + l2) * cols + c;
+                for (int l = 1; l <= l2; l++) num = fmaf((float)l, dc[l * cols] - dc[-l * cols], num);
+                val = sval = num * a.rden2;
             }
             orow[(long long)r * width] = val;
             if (t < n_stats) { // normalizercpu.cpp:31-66: double sums of float values / float products

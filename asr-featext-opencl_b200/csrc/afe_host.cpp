@@ -105,6 +105,23 @@ void build_mel_pairs(const Derived &d, const std::vector<int> &edges, const std:
         }
 }
 
+// Equivalent per-filter form of the same sweep: filter b sums, in ascending bin order, weights[b%2][j] * v[j] over
+// j in [edges[b], edges[b+2]) starting from zero (its accumulator is reset when filter b-2 closes at edges[b]).
+void build_filter_lists(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters,
+                        std::vector<int> &fidx, std::vector<float> &wlist)
+{
+    fidx.assign(3 * (size_t)d.nb, 0);
+    wlist.clear();
+    for (int b = 0; b < d.nb; b++) {
+        const int j0 = edges[b], j1 = edges[b + 2];
+        fidx[b] = j0;
+        fidx[d.nb + b] = j1 - j0;
+        fidx[2 * d.nb + b] = (int)wlist.size();
+        for (int j = j0; j < j1; j++) wlist.push_back(filters[(size_t)(b % 2) * d.N2 + j]);
+    }
+    if (wlist.empty()) wlist.push_back(0.f);
+}
+
 } // namespace afe
 
 using namespace afe;

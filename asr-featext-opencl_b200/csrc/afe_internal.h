@@ -64,6 +64,10 @@ void build_dct(const Derived &d, std::vector<float> &dct);
 void build_mel_pairs(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters,
                      std::vector<float> &pairs /* [bins][2] */);
 
+// per-filter contiguous weight lists: filter b covers bins [edges[b], edges[b+2]) with weights filters[b%2][bin]
+void build_filter_lists(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters,
+                        std::vector<int> &fidx /* [3][nb] */, std::vector<float> &wlist);
+
 // ---- device-side constant tables for the in-register FFT (afe_fft.cuh)
 struct FftTables {
     float2 *d_tw_a = nullptr;   // [R][16]   exp(-2 pi i n2 k1 / M)
@@ -78,6 +82,9 @@ struct MelTables {              // device copies, rebuilt when alpha changes
     int *d_edges = nullptr;     // [nb+2]
     float *d_pairs = nullptr;   // [bins][2]
     float *d_dct = nullptr;     // [nb][dct_len] (null when ceps_len == 0)
+    int *d_fidx = nullptr;      // [3][nb] per filter: first bin, bins, offset into wlist (fused kernel)
+    float *d_wlist = nullptr;   // concatenated per-filter weights
+    int nwl = 0;
     float *d_window = nullptr;  // [W]
     float2 *d_window2 = nullptr; // [M] (w[2n], w[2n+1]) zero padded
     float alpha_built = -1.f;

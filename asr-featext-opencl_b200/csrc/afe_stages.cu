@@ -34,24 +34,29 @@ void launch_segment(const int16_t *d_pcm, const float *d_window, float *d_out, i
 
 // ------------------------------------------------------------------------------------------------ FFT + magnitude
 // Fast path (N2 = 256/512, even S): the same in-register FFT as the fused kernel, PCM read straight from global.
-template <int N2> __global__ void __launch_bounds__(128) k_fft_mag(const int16_t *__restrict__ pcm, const float2 *window2,
-                                                                  const float2 *tw_a, const float2 *tw_p,
-                                                                  float *__restrict__ mag, int frames, int S, int nz)
+template <int N2, int NZ>
+__global__ void __launch_bounds__(128) k_fft_mag(const int16_t *__restrict__ pcm, const float2 *window2, const float2 *tw_a,
+                                                 const float2 *tw_p, float *__restrict__ mag, int frames, int S)
 {
     using C = dev::FftCfg<N2>;
     __shared__ float2 scratch[4 * C::FPW * C::SCR];
+    __shared__ float2 s_win[C::M], s_twp[C::M / 2];
+    __shared__ float s_dump[C::BINS + 3]; // magnitude row of padding frames
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lf = lane % C::R, fw = lane / C::R;
-    dev::LaneConsts<N2> lc;
-    dev::load_lane_consts<N2>(lc, window2, tw_a, tw_p, lf);
+    for (int i = threadIdx.x; i < C::M; i += blockDim.x) s_win[i] = window2[i];
+    for (int i = threadIdx.x; i < C::M / 2; i += blockDim.x) s_twp[i] = tw_p[i];
+    float2 twa[16];
+    dev::load_twa<N2>(twa, tw_a, lf);
+    __syncthreads();
     const int per_iter = 4 * C::FPW;
     for (int f0 = blockIdx.x * per_iter; f0 < frames; f0 += gridDim.x * per_iter) {
         const int f = f0 + warp * C::FPW + fw;
         const bool act = f < frames;
         const int fc = act ? f : frames - 1;
         const uint32_t *words = reinterpret_cast<const uint32_t *>(pcm + (long long)fc * S);
-        dev::fft_frame_mag<N2, false>(words, nz, lc, scratch + (warp * C::FPW + fw) * C::SCR,
-                                      act ? mag + (long long)f * C::BINS : nullptr, lf);
+        dev::fft_frame_mag<N2, NZ, false>(words, s_win, s_twp, twa, scratch + (warp * C::FPW + fw) * C::SCR,
+                                          act ? mag + (long long)f * C::BINS : s_dump, lf);
     }
 }
 
@@ -94,9 +99,14 @@ void launch_fft_mag(const Derived &d, const FftTables &ft, const MelTables &mt, 
     if (fast) {
         const int R = d.M / 16, per_iter = 4 * (32 / R);
         const int grid = std::min((frames + per_iter - 1) / per_iter, 148 * 8);
-        const int nz = std::min(16, (d.W + 2 * R - 1) / (2 * R));
-        if (d.N2 == 512) k_fft_mag<512><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, nz);
-        else k_fft_mag<256><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, nz);
+        const bool pruned = d.W <= 26 * R;
+        if (d.N2 == 512) {
+            if (pruned) k_fft_mag<512, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+            else k_fft_mag<512, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+        } else {
+            if (pruned) k_fft_mag<256, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+            else k_fft_mag<256, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+        }
     } else {
         if (d.N2 > 4096) throw Error("window_size above 4096 is not supported");
         const int threads = std::max(32, std::min(256, d.N2 / 2));
