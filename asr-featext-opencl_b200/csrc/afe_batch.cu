@@ -50,7 +50,8 @@ void MelTables::release()
     if (d_window2) cudaFree(d_window2);
     if (d_fidx) cudaFree(d_fidx);
     if (d_wlist) cudaFree(d_wlist);
-    d_fidx = nullptr; d_wlist = nullptr; nwl = 0;
+    if (d_dct16) cudaFree(d_dct16);
+    d_fidx = nullptr; d_wlist = nullptr; d_dct16 = nullptr; nwl = 0;
     d_edges = nullptr; d_pairs = nullptr; d_dct = nullptr; d_window = nullptr; d_window2 = nullptr;
     alpha_built = -1.f;
 }
@@ -66,7 +67,7 @@ void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t
     build_filter_lists(d, edges, filters, fidx, wlist);
     if (!t.d_fidx) AFE_CUDA(cudaMalloc(&t.d_fidx, sizeof(int) * fidx.size()));
     if (t.d_wlist && (int)wlist.size() > t.nwl) { cudaFree(t.d_wlist); t.d_wlist = nullptr; }
-    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins)));
+    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins + 8 * (size_t)d.nb)));
     t.nwl = (int)wlist.size();
     AFE_CUDA(cudaMemcpyAsync(t.d_fidx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice, st));
     AFE_CUDA(cudaMemcpyAsync(t.d_wlist, wlist.data(), sizeof(float) * wlist.size(), cudaMemcpyHostToDevice, st));
@@ -75,10 +76,18 @@ void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t
     // pageable source + stream-ordered copy: cudaMemcpyAsync from pageable memory stages synchronously, safe with locals
     AFE_CUDA(cudaMemcpyAsync(t.d_edges, edges.data(), sizeof(int) * (d.nb + 2), cudaMemcpyHostToDevice, st));
     AFE_CUDA(cudaMemcpyAsync(t.d_pairs, pairs.data(), sizeof(float) * 2 * d.bins, cudaMemcpyHostToDevice, st));
+    std::vector<float> dct16;
     if (d.C > 0 && !t.d_dct) {
         build_dct(d, dct);
         AFE_CUDA(cudaMalloc(&t.d_dct, sizeof(float) * dct.size()));
         AFE_CUDA(cudaMemcpyAsync(t.d_dct, dct.data(), sizeof(float) * dct.size(), cudaMemcpyHostToDevice, st));
+        if (d.dct_len <= 16) {
+            dct16.assign((size_t)d.nb * 16, 0.f);
+            for (int k = 0; k < d.nb; k++)
+                for (int j = 0; j < d.dct_len; j++) dct16[(size_t)k * 16 + j] = dct[(size_t)k * d.dct_len + j];
+            AFE_CUDA(cudaMalloc(&t.d_dct16, sizeof(float) * dct16.size()));
+            AFE_CUDA(cudaMemcpyAsync(t.d_dct16, dct16.data(), sizeof(float) * dct16.size(), cudaMemcpyHostToDevice, st));
+        }
     }
     AFE_CUDA(cudaStreamSynchronize(st));
     t.alpha_built = alpha;
@@ -208,8 +217,9 @@ static void check_fused_support(const Derived &d)
 template <int N2> static FusedSmem layout_for(const afe_batch *b)
 {
     const Derived &d = b->d;
-    // wlist never exceeds 2 entries per bin (each bin feeds a rising and a falling side)
-    return fused_smem_layout<N2>(d.S, d.nb, 2 * d.bins, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max, d.l2);
+    // wlist: <= 2 entries per bin (rising + falling side) plus <= 6 floats of alignment padding per filter
+    return fused_smem_layout<N2>(d.S, d.nb, 2 * d.bins + 8 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
+                                 d.l2, d.width / d.cols);
 }
 
 template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
@@ -218,7 +228,7 @@ template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *
     FusedArgs a{};
     a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles;
     a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.fidx = b->mel.d_fidx; a.wlist = b->mel.d_wlist; a.nwl = b->mel.nwl; a.dct = b->mel.d_dct;
+    a.fidx = b->mel.d_fidx; a.wlist = b->mel.d_wlist; a.nwl = b->mel.nwl; a.dct = b->mel.d_dct16;
     a.partials = want_stats ? b->d_partials : nullptr;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
@@ -233,7 +243,8 @@ template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
-    if (a.nwl > 2 * d.bins) throw Error("mel weight list exceeds its shared-memory budget");
+    if (a.nwl > 2 * d.bins + 8 * d.nb) throw Error("mel weight list exceeds its shared-memory budget");
+    a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
     auto kern = fast ? k_fused_mfcc<N2, NZ, true> : k_fused_mfcc<N2, NZ, false>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));

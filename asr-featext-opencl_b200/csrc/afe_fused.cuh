@@ -38,14 +38,15 @@ struct FusedArgs {
     float *out;
     const Tile *tiles;
     const float2 *window2, *tw_a, *tw_p;
-    const int *fidx;     // [3][nb]: per filter first bin, number of bins, offset into wlist
-    const float *wlist;  // concatenated triangular weights, filter by filter
-    const float *dct;
+    const int *fidx;     // [3][nb]: per filter first bin (multiple of 4), float4 chunks, offset into wlist (float4 units)
+    const float *wlist;  // concatenated triangular weights, filter by filter, zero padded to the float4 grid
+    const float *dct;    // [nb][16] DCT rows zero padded to 16 columns
     double *partials;    // [ntiles][width][4] or nullptr
     int W, S, nb, dct_len, cols, width, l1, l2, nstreams, nwl;
     int q1;              // reproduce the single-block flush quirk
     int use_tma;
     int stats_rows_mode; // 0: no stats, 1: rows < T-D, 2: all rows
+    int stats_kind;      // 0: none, 1: sums (CMN), 2: + sums of squares (CVN), 3: + min/max (MINMAX)
     int tc_max;          // capacity (frames) of the cepstra tile
     float rden1, rden2;  // 1 / (2*sum(l^2))
 };
@@ -57,13 +58,13 @@ constexpr int kMagStride = 260; // floats per magnitude row: = 4 (mod 32), so ph
 
 struct FusedSmem {
     int off_mbar, off_win, off_twp, off_fidx, off_wlist, off_dct, off_warp, warp_bytes, w_pcm, w_scratch, w_mags,
-        pcm_bytes, off_red, off_cep, total;
+        pcm_bytes, off_dd, off_red, off_cep, total;
 };
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int N2>
-FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int tc_max, int nout_max, int l2)
+FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int tc_max, int nout_max, int l2, int nstreams)
 {
     using C = dev::FftCfg<N2>;
     FusedSmem L;
@@ -73,7 +74,7 @@ FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int t
     L.off_twp = o; o += align_up(C::M / 2 * 8, 16);
     L.off_fidx = o; o += align_up(3 * nb * 4, 16);
     L.off_wlist = o; o += align_up(nwl * 4, 16);
-    L.off_dct = o; o += align_up((dct_len > 0 ? nb * dct_len : 1) * 4, 16);
+    L.off_dct = o; o += align_up((dct_len > 0 ? nb * 16 : 1) * 4, 16);
     // per warp: [pcm | scratch | mags]
     int w = 0;
     L.pcm_bytes = align_up(((kRound - 1) * S + N2) * 2, 16) + 16;
@@ -81,12 +82,14 @@ FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int t
     L.w_scratch = w; w += align_up(C::FPW * C::SCR * 8, 16);
     L.w_mags = w; w += align_up(kRound * kMagStride * 4, 16);
     L.warp_bytes = align_up(w, 128);
-    // phase 3 reuses the per-warp area: [delta rows | reduction scratch]
-    const int dhat = align_up((nout_max + 2 * l2) * cols * 4, 16);
-    const int phase3 = dhat + kFusedThreads * 4 * 8;
+    // phase 3 reuses the per-warp area: [delta rows | delta-delta rows | reduction scratch]
+    const int dhat = nstreams >= 2 ? align_up((nout_max + 2 * l2) * cols * 4, 16) : 0;
+    const int dd = nstreams >= 3 ? align_up(nout_max * cols * 4, 16) : 0;
+    const int phase3 = dhat + dd + kFusedThreads * 4 * 8;
     o = align_up(o, 128);
     L.off_warp = o;
-    L.off_red = o + dhat;
+    L.off_dd = o + dhat;
+    L.off_red = o + dhat + dd;
     o += align_up(kFusedWarps * L.warp_bytes > phase3 ? kFusedWarps * L.warp_bytes : phase3, 128);
     L.off_cep = o; o += align_up(tc_max * cols * 4, 16);
     L.total = o;
@@ -182,9 +185,11 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
     for (int i = tid; i < 3 * a.nb; i += kFusedThreads) s_fstart[i] = a.fidx[i];
     for (int i = tid; i < a.nwl; i += kFusedThreads) s_wlist[i] = a.wlist[i];
     if (a.dct_len > 0)
-        for (int i = tid; i < a.nb * a.dct_len; i += kFusedThreads) s_dct[i] = a.dct[i];
+        for (int i = tid; i < a.nb * 16; i += kFusedThreads) s_dct[i] = a.dct[i];
     float2 twa[16];
     dev::load_twa<N2>(twa, a.tw_a, lf);
+    // the 128-bit mel loads may touch the 3 pad floats behind bin M of a magnitude row (with zero weights): keep them finite
+    if (lane < kRound * 3) w_mags[(lane / 3) * MS + M + 1 + lane % 3] = 0.f;
     __syncthreads();
 
     const int f2 = lane >> 2, q = lane & 3; // phase 2: frame within the round, lane within the frame
@@ -222,7 +227,8 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
             dev::mbar_expect_tx(w_mbar, bytes);
             dev::tma_bulk_g2s(w_pcm, upcm + (long long)(r + kFusedWarps) * kRound * a.S, bytes, w_mbar);
         }
-        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+4, ... of frame f2
+        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+4, ... of frame f2. 128-bit loads of the
+        //      magnitudes and of the zero-padded weight list (both on the 4-bin grid), 4 partial sums per filter.
         {
             const float *mrow = w_mags + f2 * MS;
             float cep[16];
@@ -232,28 +238,40 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
             const bool live = f0 + f2 < ncomp;
             for (int b = q; b < a.nb; b += 4) {
                 const int n = s_flen[b];
-                const float *mv = mrow + s_fstart[b];
-                const float *wv = s_wlist + s_woff[b];
-                float acc = 0.f;
-                for (int i = 0; i < n; i++) acc = fmaf(wv[i], mv[i], acc);
-                const float e = dev::mel_log<FAST>(acc);
+                const float4 *mv = reinterpret_cast<const float4 *>(mrow + s_fstart[b]);
+                const float4 *wv = reinterpret_cast<const float4 *>(s_wlist) + s_woff[b];
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+                for (int i = 0; i < n; i++) {
+                    const float4 m = mv[i], w = wv[i];
+                    a0 = fmaf(w.x, m.x, a0); a1 = fmaf(w.y, m.y, a1);
+                    a2 = fmaf(w.z, m.z, a2); a3 = fmaf(w.w, m.w, a3);
+                }
+                const float e = dev::mel_log<FAST>((a0 + a1) + (a2 + a3));
                 if (a.dct_len > 0) {
-                    const float *row = s_dct + b * a.dct_len;
+                    const float4 *row = reinterpret_cast<const float4 *>(s_dct + b * 16);
 #pragma unroll
-                    for (int c = 0; c < 16; c++)
-                        if (c < a.dct_len) cep[c] = fmaf(e, row[c], cep[c]);
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 d4 = row[c4];
+                        cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
+                        cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
+                        cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
+                        cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
+                    }
                 } else if (live)
                     crow[b] = e;
             }
             if (a.dct_len > 0) {
+                // sum the 4 lanes of a frame; lane q then holds columns c = q (mod 4) in cep[4*j + q]
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
-                    if (c < a.dct_len) {
-                        float v = cep[c];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        if (live && (c & 3) == q) crow[c] = v;
-                    }
+                    cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 1);
+                    cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 2);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float v = q == 0 ? cep[4 * j] : q == 1 ? cep[4 * j + 1] : q == 2 ? cep[4 * j + 2] : cep[4 * j + 3];
+                    if (live && 4 * j + q < a.dct_len) crow[4 * j + q] = v;
                 }
             }
         }
@@ -261,59 +279,66 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
     }
     __syncthreads();
 
-    // ---- phase 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
+    // ---- phase 3: every thread owns ONE column (c = tid % cols / col = tid % width) and strides over rows, so the loops
+    //      are uniform (no integer division, no stream-dependent branch inside them).
     float *s_dhat = reinterpret_cast<float *>(smem + L.off_warp);
+    float *s_dd = reinterpret_cast<float *>(smem + L.off_dd);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;
     if (a.nstreams >= 2) {
+        // 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
+        const int rp = kFusedThreads / cols, rl = tid / cols, c = tid - rl * cols;
         const int nd = nout + 2 * l2;
-        for (int idx = tid; idx < nd * cols; idx += kFusedThreads) {
-            const int i = idx / cols, c = idx - i * cols;
-            const int u = t0 - l2 + i;
-            float num = 0.f;
-            for (int l = 1; l <= l1; l++) {
-                const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
-                const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
-                num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
+        if (rl < rp) {
+            for (int i = rl; i < nd; i += rp) {
+                const int u = t0 - l2 + i;
+                float num = 0.f;
+                for (int l = 1; l <= l1; l++) {
+                    const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
+                    const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
+                    num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
+                }
+                s_dhat[i * cols + c] = num * a.rden1;
             }
-            s_dhat[idx] = num * a.rden1;
         }
         __syncthreads();
+        if (a.nstreams >= 3) { // 3b: delta-delta of the extended delta rows
+            if (rl < rp) {
+                for (int r = rl; r < nout; r += rp) {
+                    const float *dc = s_dhat + (r + l2) * cols + c;
+                    float num = 0.f;
+                    for (int l = 1; l <= l2; l++) num = fmaf((float)l, dc[l * cols] - dc[-l * cols], num);
+                    s_dd[r * cols + c] = num * a.rden2;
+                }
+            }
+            __syncthreads();
+        }
     }
 
-    // ---- phase 3b: rows out, column statistics
+    // 3c: rows out (coalesced: consecutive threads write consecutive floats), column statistics
     const int width = a.width;
     const int rpp = kFusedThreads / width; // rows per pass (width <= 128 enforced by the host)
     const bool active = tid < rpp * width;
     const int r_off = tid / width, col = tid - r_off * width;
     const int strm = col / cols, c = col - strm * cols;
     const int n_stats = a.stats_rows_mode == 1 ? T - D : (a.stats_rows_mode == 2 ? T : 0);
+    // source of this thread's column: src[r * cols]; statics of the Q1 rows come from D rows earlier
+    const float *src = strm == 0 ? s_cep + (t0 - c0f) * cols + c : strm == 1 ? s_dhat + l2 * cols + c : s_dd + c;
+    const int rq = (a.q1 && strm == 0) ? max(0, T - D - t0) : nout; // first row written with the shifted static
+    const int rs = min(nout, max(0, n_stats - t0));                 // rows [0, rs) enter the statistics
     double sum = 0.0, sumsq = 0.0;
     float mn = FLT_MAX, mx = -FLT_MAX;
     if (active) {
         float *orow = a.out + (tl.out_row0 + t0) * (long long)width + col;
         for (int r = r_off; r < nout; r += rpp) {
-            const int t = t0 + r;
-            float val, sval; // sval: the value the statistics see
-            if (strm == 0) {
-                // Q1 shifts only what is WRITTEN for the flushed rows; the reference takes its statistics on the
-                // first block's own statics (mfcccpu.cpp:274 / :383-384), i.e. always un-shifted
-                sval = s_cep[(t - c0f) * cols + c];
-                val = (a.q1 && t >= T - D) ? s_cep[(t - D - c0f) * cols + c] : sval;
-            } else if (strm == 1) {
-                val = sval = s_dhat[(r + l2) * cols + c];
-            } else {
-                float num = 0.f;
-                const float *dc = s_dhat + (r + l2) * cols + c;
-                for (int l = 1; l <= l2; l++) num = fmaf((float)l, dc[l * cols] - dc[-l * cols], num);
-                val = sval = num * a.rden2;
-            }
-            orow[(long long)r * width] = val;
-            if (t < n_stats) { // normalizercpu.cpp:31-66: double sums of float values / float products
-                sum += (double)sval;
-                sumsq += (double)__fmul_rn(sval, sval);
-                mn = fminf(mn, sval);
-                mx = fmaxf(mx, sval);
+            const float sval = src[r * cols];
+            // Q1 shifts only what is WRITTEN for the flushed rows; the reference takes its statistics on the first
+            // block's own statics (mfcccpu.cpp:274 / :383-384), i.e. always un-shifted
+            orow[(long long)r * width] = r >= rq ? src[(r - D) * cols] : sval;
+            if (r < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
+                if (a.stats_kind >= 1) sum += (double)sval;
+                if (a.stats_kind >= 2) sumsq += (double)__fmul_rn(sval, sval);
+                if (a.stats_kind >= 3) { mn = fminf(mn, sval); mx = fmaxf(mx, sval); }
             }
         }
     }

@@ -105,8 +105,10 @@ void build_mel_pairs(const Derived &d, const std::vector<int> &edges, const std:
         }
 }
 
-// Equivalent per-filter form of the same sweep: filter b sums, in ascending bin order, weights[b%2][j] * v[j] over
-// j in [edges[b], edges[b+2]) starting from zero (its accumulator is reset when filter b-2 closes at edges[b]).
+// Equivalent per-filter form of the same sweep: filter b sums weights[b%2][j] * v[j] over j in [edges[b], edges[b+2])
+// starting from zero (its accumulator is reset when filter b-2 closes at edges[b]). For 128-bit shared-memory loads
+// every list starts at a bin that is a multiple of 4 and is zero padded to a multiple of 4 weights:
+// fidx = [first bin (multiple of 4) | number of float4 chunks | offset into wlist in float4 units], each [nb].
 void build_filter_lists(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters,
                         std::vector<int> &fidx, std::vector<float> &wlist)
 {
@@ -114,12 +116,14 @@ void build_filter_lists(const Derived &d, const std::vector<int> &edges, const s
     wlist.clear();
     for (int b = 0; b < d.nb; b++) {
         const int j0 = edges[b], j1 = edges[b + 2];
-        fidx[b] = j0;
-        fidx[d.nb + b] = j1 - j0;
-        fidx[2 * d.nb + b] = (int)wlist.size();
-        for (int j = j0; j < j1; j++) wlist.push_back(filters[(size_t)(b % 2) * d.N2 + j]);
+        const int s4 = j0 & ~3, n4 = j1 > j0 ? (j1 - s4 + 3) / 4 : 0;
+        fidx[b] = s4;
+        fidx[d.nb + b] = n4;
+        fidx[2 * d.nb + b] = (int)wlist.size() / 4;
+        for (int j = s4; j < s4 + 4 * n4; j++)
+            wlist.push_back(j >= j0 && j < j1 ? filters[(size_t)(b % 2) * d.N2 + j] : 0.f);
     }
-    if (wlist.empty()) wlist.push_back(0.f);
+    if (wlist.empty()) wlist.assign(4, 0.f);
 }
 
 } // namespace afe

@@ -83,7 +83,8 @@ struct MelTables {              // device copies, rebuilt when alpha changes
     float *d_pairs = nullptr;   // [bins][2]
     float *d_dct = nullptr;     // [nb][dct_len] (null when ceps_len == 0)
     int *d_fidx = nullptr;      // [3][nb] per filter: first bin, bins, offset into wlist (fused kernel)
-    float *d_wlist = nullptr;   // concatenated per-filter weights
+    float *d_wlist = nullptr;   // concatenated per-filter weights, float4 aligned / padded
+    float *d_dct16 = nullptr;   // [nb][16] DCT rows zero padded to 16 columns (fused kernel, LDS.128)
     int nwl = 0;
     float *d_window = nullptr;  // [W]
     float2 *d_window2 = nullptr; // [M] (w[2n], w[2n+1]) zero padded
