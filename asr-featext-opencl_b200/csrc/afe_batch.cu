@@ -184,6 +184,7 @@ struct afe_batch {
     double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
+    int shape_warps = 8, shape_round = 4;   // kernel shape, see afe_fused.cuh (AFE_FUSED_SHAPE=4x8 selects the other one)
     FusedSmem L{};
     int last_launches = 0;
     // host staging for run_host
@@ -206,6 +207,7 @@ struct afe_batch {
 
 static void check_fused_support(const Derived &d)
 {
+    const int kFusedThreads = 128; // the smaller of the two kernel shapes bounds the output width
     if (d.N2 != 512 && d.N2 != 256)
         throw Error("fused batch path supports 256/512-point FFTs (window_size 129..512); use the streaming object");
     if (d.S % 2) throw Error("fused batch path needs an even shift");
@@ -218,11 +220,12 @@ template <int N2> static FusedSmem layout_for(const afe_batch *b)
 {
     const Derived &d = b->d;
     // wlist: <= 2 entries per bin (rising + falling side) plus <= 6 floats of alignment padding per filter
-    return fused_smem_layout<N2>(d.S, d.nb, 2 * d.bins + 8 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
+    return fused_smem_layout<N2>(b->shape_warps, b->shape_round, d.S, d.nb, 2 * d.bins + 8 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
                                  d.l2, d.width / d.cols);
 }
 
-template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+template <int N2, int NZ, int WARPS, int ROUND>
+static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
 {
     const Derived &d = b->d;
     FusedArgs a{};
@@ -246,9 +249,9 @@ template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *
     if (a.nwl > 2 * d.bins + 8 * d.nb) throw Error("mel weight list exceeds its shared-memory budget");
     a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, NZ, true> : k_fused_mfcc<N2, NZ, false>;
+    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, ROUND> : k_fused_mfcc<N2, NZ, false, WARPS, ROUND>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    kern<<<b->n_tiles, kFusedThreads, b->L.total, b->stream>>>(a, b->L);
+    kern<<<b->n_tiles, 32 * WARPS, b->L.total, b->stream>>>(a, b->L);
     AFE_CUDA(cudaGetLastError());
     count_launch();
     b->last_launches++;
@@ -263,8 +266,17 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    if (b->d.N2 == 512) pruned ? launch_fused<512, 13>(b, d_pcm, d_out, want_stats) : launch_fused<512, 16>(b, d_pcm, d_out, want_stats);
-    else pruned ? launch_fused<256, 13>(b, d_pcm, d_out, want_stats) : launch_fused<256, 16>(b, d_pcm, d_out, want_stats);
+    const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->shape_warps == 8 ? 1 : 0);
+    switch (key) {
+    case 0: launch_fused<512, 13, 4, 8>(b, d_pcm, d_out, want_stats); break;
+    case 1: launch_fused<512, 13, 8, 4>(b, d_pcm, d_out, want_stats); break;
+    case 2: launch_fused<512, 16, 4, 8>(b, d_pcm, d_out, want_stats); break;
+    case 3: launch_fused<512, 16, 8, 4>(b, d_pcm, d_out, want_stats); break;
+    case 4: launch_fused<256, 13, 4, 8>(b, d_pcm, d_out, want_stats); break;
+    case 5: launch_fused<256, 13, 8, 4>(b, d_pcm, d_out, want_stats); break;
+    case 6: launch_fused<256, 16, 4, 8>(b, d_pcm, d_out, want_stats); break;
+    default: launch_fused<256, 16, 8, 4>(b, d_pcm, d_out, want_stats); break;
+    }
 }
 
 static void run_reduce(afe_batch *b)
@@ -358,6 +370,10 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         DeviceGuard g(b->device);
         b->free_plan();
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
+        const char *env_shape = getenv("AFE_FUSED_SHAPE");
+        if (env_shape && !strcmp(env_shape, "4x8")) { b->shape_warps = 4; b->shape_round = 8; }
+        else if (env_shape && !strcmp(env_shape, "8x4")) { b->shape_warps = 8; b->shape_round = 4; }
+        const int kRound = b->shape_round;
         const char *env_tc = getenv("AFE_TILE_FRAMES");
         int tc = env_tc ? atoi(env_tc) : 264;
         tc = std::min(tc, (4096 / d.cols) / kRound * kRound);

@@ -51,10 +51,12 @@ struct FusedArgs {
     float rden1, rden2;  // 1 / (2*sum(l^2))
 };
 
-constexpr int kFusedWarps = 4;
-constexpr int kFusedThreads = 32 * kFusedWarps;
-constexpr int kRound = 8;       // frames per warp round
-constexpr int kMagStride = 260; // floats per magnitude row: = 4 (mod 32), so phase 2's 8 frames x 4 lanes hit 32 banks
+// Kernel shape: WARPS warps per CTA, each owning rounds of ROUND frames; phase 2 runs 32/ROUND lanes per frame.
+//   <4, 8>: 4 lanes per frame in phase 2 (cheapest mel), 16 KB of shared memory per warp
+//   <8, 4>: 8 lanes per frame, 10.6 KB per warp -> twice the resident warps per SM
+// Magnitude row stride (floats): a multiple of 4 (128-bit loads) chosen so that the rows written by one FFT call
+// (ROUND/FPW rows apart) start 16 banks (N2=512) / 8 banks (N2=256) apart.
+__host__ __device__ constexpr int mag_stride(int round) { return round == 8 ? 260 : 264; }
 
 struct FusedSmem {
     int off_mbar, off_win, off_twp, off_fidx, off_wlist, off_dct, off_warp, warp_bytes, w_pcm, w_scratch, w_mags,
@@ -64,8 +66,10 @@ struct FusedSmem {
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int N2>
-FusedSmem fused_smem_layout(int S, int nb, int nwl, int dct_len, int cols, int tc_max, int nout_max, int l2, int nstreams)
+FusedSmem fused_smem_layout(int kFusedWarps, int kRound, int S, int nb, int nwl, int dct_len, int cols, int tc_max,
+                            int nout_max, int l2, int nstreams)
 {
+    const int kFusedThreads = 32 * kFusedWarps, kMagStride = mag_stride(kRound);
     using C = dev::FftCfg<N2>;
     FusedSmem L;
     int o = 0;
@@ -137,12 +141,15 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 } // namespace dev
 
-template <int N2, int NZ, bool FAST>
-__global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs a, const FusedSmem L)
+template <int N2, int NZ, bool FAST, int kFusedWarps, int kRound>
+__global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_fused_mfcc(const FusedArgs a, const FusedSmem L)
 {
     using C = dev::FftCfg<N2>;
-    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, M = C::M, MS = kMagStride;
+    constexpr int kFusedThreads = 32 * kFusedWarps;
+    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, M = C::M, MS = mag_stride(kRound);
     constexpr int ITERS = kRound / FPW; // FFT calls per round
+    constexpr int TPF = 32 / kRound;    // phase-2 lanes per frame
+    static_assert(kRound % FPW == 0 && (TPF == 4 || TPF == 8), "unsupported kernel shape");
     extern __shared__ __align__(128) unsigned char smem[];
     float2 *s_win = reinterpret_cast<float2 *>(smem + L.off_win);
     float2 *s_twp = reinterpret_cast<float2 *>(smem + L.off_twp);
@@ -189,10 +196,10 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
     float2 twa[16];
     dev::load_twa<N2>(twa, a.tw_a, lf);
     // the 128-bit mel loads may touch the 3 pad floats behind bin M of a magnitude row (with zero weights): keep them finite
-    if (lane < kRound * 3) w_mags[(lane / 3) * MS + M + 1 + lane % 3] = 0.f;
+    if (lane < kRound * 3) w_mags[(lane / 3) * MS + M + 1 + lane % 3] = 0.f; // (bins M+4.. are never loaded: last chunk ends <= M+3)
     __syncthreads();
 
-    const int f2 = lane >> 2, q = lane & 3; // phase 2: frame within the round, lane within the frame
+    const int f2 = lane / TPF, q = lane % TPF; // phase 2: frame within the round, lane within the frame
     uint32_t parity = 0;
     for (int r = warp; r < nrounds; r += kFusedWarps) {
         const int f0 = r * kRound;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
             dev::mbar_expect_tx(w_mbar, bytes);
             dev::tma_bulk_g2s(w_pcm, upcm + (long long)(r + kFusedWarps) * kRound * a.S, bytes, w_mbar);
         }
-        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+4, ... of frame f2. 128-bit loads of the
+        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+TPF, ... of frame f2. 128-bit loads of the
         //      magnitudes and of the zero-padded weight list (both on the 4-bin grid), 4 partial sums per filter.
         {
             const float *mrow = w_mags + f2 * MS;
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
             float *crow = s_cep + (f0 + f2) * cols;
             const bool live = f0 + f2 < ncomp;
-            for (int b = q; b < a.nb; b += 4) {
+            for (int b = q; b < a.nb; b += TPF) {
                 const int n = s_flen[b];
                 const float4 *mv = reinterpret_cast<const float4 *>(mrow + s_fstart[b]);
                 const float4 *wv = reinterpret_cast<const float4 *>(s_wlist) + s_woff[b];
@@ -262,17 +269,16 @@ __global__ void __launch_bounds__(kFusedThreads, 3) k_fused_mfcc(const FusedArgs
                     crow[b] = e;
             }
             if (a.dct_len > 0) {
-                // sum the 4 lanes of a frame; lane q then holds columns c = q (mod 4) in cep[4*j + q]
+                // sum over the TPF lanes of a frame; lane q then writes the columns c = q (mod TPF)
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 1);
                     cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 2);
+                    if (TPF == 8) cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 4);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v = q == 0 ? cep[4 * j] : q == 1 ? cep[4 * j + 1] : q == 2 ? cep[4 * j + 2] : cep[4 * j + 3];
-                    if (live && 4 * j + q < a.dct_len) crow[4 * j + q] = v;
-                }
+                for (int c = 0; c < 16; c++)
+                    if ((c % TPF) == q && live && c < a.dct_len) crow[c] = cep[c];
             }
         }
         __syncwarp(); // mags are rewritten by the next round's phase 1
