@@ -56,7 +56,7 @@ void MelTables::release()
     alpha_built = -1.f;
 }
 
-void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st)
+void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st, int tpf)
 {
     std::vector<int> edges, fidx; std::vector<float> filters, pairs, dct, wlist;
     build_filters(d, alpha, edges, filters);
@@ -64,13 +64,18 @@ void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t
         if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     build_mel_pairs(d, edges, filters, pairs);
-    build_filter_lists(d, edges, filters, fidx, wlist);
+    t.tpf = tpf;
+    if (tpf > 0) { // only the fused kernel uses the per-filter lists
+    int max_bin = 0;
+    build_filter_lists(d, edges, filters, tpf, fidx, wlist, max_bin);
+    if (max_bin > kMagRow) throw Error("mel filter too wide for the fused kernel's magnitude rows");
     if (!t.d_fidx) AFE_CUDA(cudaMalloc(&t.d_fidx, sizeof(int) * fidx.size()));
     if (t.d_wlist && (int)wlist.size() > t.nwl) { cudaFree(t.d_wlist); t.d_wlist = nullptr; }
-    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins + 8 * (size_t)d.nb)));
+    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins + 36 * (size_t)d.nb)));
     t.nwl = (int)wlist.size();
     AFE_CUDA(cudaMemcpyAsync(t.d_fidx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice, st));
     AFE_CUDA(cudaMemcpyAsync(t.d_wlist, wlist.data(), sizeof(float) * wlist.size(), cudaMemcpyHostToDevice, st));
+    }
     if (!t.d_edges) AFE_CUDA(cudaMalloc(&t.d_edges, sizeof(int) * (d.nb + 2)));
     if (!t.d_pairs) AFE_CUDA(cudaMalloc(&t.d_pairs, sizeof(float) * 2 * d.bins));
     // pageable source + stream-ordered copy: cudaMemcpyAsync from pageable memory stages synchronously, safe with locals
@@ -220,7 +225,7 @@ template <int N2> static FusedSmem layout_for(const afe_batch *b)
 {
     const Derived &d = b->d;
     // wlist: <= 2 entries per bin (rising + falling side) plus <= 6 floats of alignment padding per filter
-    return fused_smem_layout<N2>(b->shape_warps, b->shape_round, d.S, d.nb, 2 * d.bins + 8 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
+    return fused_smem_layout<N2>(b->shape_warps, b->shape_round, d.S, d.nb, 2 * d.bins + 36 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
                                  d.l2, d.width / d.cols);
 }
 
@@ -246,7 +251,7 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
-    if (a.nwl > 2 * d.bins + 8 * d.nb) throw Error("mel weight list exceeds its shared-memory budget");
+    if (a.nwl > 2 * d.bins + 36 * d.nb) throw Error("mel weight list exceeds its shared-memory budget");
     a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
     auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, ROUND> : k_fused_mfcc<N2, NZ, false, WARPS, ROUND>;
@@ -261,7 +266,8 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
 {
     if (!b->window_set) throw Error("set_window must be called before running");
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
-    if (b->mel.alpha_built != b->alpha) upload_mel_tables(b->d, b->alpha, b->mel, b->stream);
+    const int tpf = 32 / b->shape_round;
+    if (b->mel.alpha_built != b->alpha || b->mel.tpf != tpf) upload_mel_tables(b->d, b->alpha, b->mel, b->stream, tpf);
     b->last_launches = 0;
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;

@@ -54,9 +54,11 @@ struct FusedArgs {
 // Kernel shape: WARPS warps per CTA, each owning rounds of ROUND frames; phase 2 runs 32/ROUND lanes per frame.
 //   <4, 8>: 4 lanes per frame in phase 2 (cheapest mel), 16 KB of shared memory per warp
 //   <8, 4>: 8 lanes per frame, 10.6 KB per warp -> twice the resident warps per SM
-// Magnitude row stride (floats): a multiple of 4 (128-bit loads) chosen so that the rows written by one FFT call
-// (ROUND/FPW rows apart) start 16 banks (N2=512) / 8 banks (N2=256) apart.
-__host__ __device__ constexpr int mag_stride(int round) { return round == 8 ? 260 : 264; }
+// Magnitude row stride: 272 floats = 68 16-byte chunks. 272 = 16 (mod 32): the two rows written by one FFT call (adjacent
+// frames) land 16 banks apart, and 68 = 4 (mod 8): in phase 2 the TPF lanes of a frame read TPF consecutive chunks and
+// the next frame's lanes the chunks 4 further (mod 8), so a quarter warp always covers 8 distinct chunk groups.
+// Columns M+1..271 are zero (weights there are zero padding; keeps 0*garbage from making NaNs).
+__host__ __device__ constexpr int mag_stride(int) { return 272; }
 
 struct FusedSmem {
     int off_mbar, off_win, off_twp, off_fidx, off_wlist, off_dct, off_warp, warp_bytes, w_pcm, w_scratch, w_mags,
@@ -76,7 +78,7 @@ FusedSmem fused_smem_layout(int kFusedWarps, int kRound, int S, int nb, int nwl,
     L.off_mbar = o; o += align_up(kFusedWarps * 8, 16); // one mbarrier per warp, never aliased
     L.off_win = o; o += align_up(C::M * 8, 16);
     L.off_twp = o; o += align_up(C::M / 2 * 8, 16);
-    L.off_fidx = o; o += align_up(3 * nb * 4, 16);
+    L.off_fidx = o; o += nb * 16;
     L.off_wlist = o; o += align_up(nwl * 4, 16);
     L.off_dct = o; o += align_up((dct_len > 0 ? nb * 16 : 1) * 4, 16);
     // per warp: [pcm | scratch | mags]
@@ -153,8 +155,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_
     extern __shared__ __align__(128) unsigned char smem[];
     float2 *s_win = reinterpret_cast<float2 *>(smem + L.off_win);
     float2 *s_twp = reinterpret_cast<float2 *>(smem + L.off_twp);
-    int *s_fstart = reinterpret_cast<int *>(smem + L.off_fidx);
-    int *s_flen = s_fstart + a.nb, *s_woff = s_flen + a.nb;
+    int4 *s_fidx4 = reinterpret_cast<int4 *>(smem + L.off_fidx);
     float *s_wlist = reinterpret_cast<float *>(smem + L.off_wlist);
     float *s_dct = reinterpret_cast<float *>(smem + L.off_dct);
     float *s_cep = reinterpret_cast<float *>(smem + L.off_cep);
@@ -189,14 +190,14 @@ __global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_
     }
     for (int i = tid; i < M; i += kFusedThreads) s_win[i] = a.window2[i];
     for (int i = tid; i < M / 2; i += kFusedThreads) s_twp[i] = a.tw_p[i];
-    for (int i = tid; i < 3 * a.nb; i += kFusedThreads) s_fstart[i] = a.fidx[i];
+    for (int i = tid; i < a.nb; i += kFusedThreads) s_fidx4[i] = reinterpret_cast<const int4 *>(a.fidx)[i];
     for (int i = tid; i < a.nwl; i += kFusedThreads) s_wlist[i] = a.wlist[i];
     if (a.dct_len > 0)
         for (int i = tid; i < a.nb * 16; i += kFusedThreads) s_dct[i] = a.dct[i];
     float2 twa[16];
     dev::load_twa<N2>(twa, a.tw_a, lf);
     // the 128-bit mel loads may touch the 3 pad floats behind bin M of a magnitude row (with zero weights): keep them finite
-    if (lane < kRound * 3) w_mags[(lane / 3) * MS + M + 1 + lane % 3] = 0.f; // (bins M+4.. are never loaded: last chunk ends <= M+3)
+    for (int i = lane; i < kRound * (MS - M - 1); i += 32) w_mags[(i / (MS - M - 1)) * MS + M + 1 + i % (MS - M - 1)] = 0.f;
     __syncthreads();
 
     const int f2 = lane / TPF, q = lane % TPF; // phase 2: frame within the round, lane within the frame
@@ -220,10 +221,11 @@ __global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_
                 for (int i = lane; i < n; i += 32) dst[i] = src[i];
             __syncwarp();
         }
-        // ---- phase 1: FFT + magnitude. Call `it` transforms frames it + fw*ITERS of the round (rows 16 banks apart)
+        // ---- phase 1: FFT + magnitude. Call `it` transforms the adjacent frames it*FPW + fw of the round: their PCM
+        //      (S/2 words apart) and their magnitude rows (272 floats apart) start 16 / 8 banks apart
 #pragma unroll 1
         for (int it = 0; it < ITERS; it++) {
-            const int fl = it + fw * ITERS;
+            const int fl = it * FPW + fw;
             const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
             dev::fft_frame_mag<N2, NZ, true>(words, s_win, s_twp, twa, w_scratch + fw * SCR, w_mags + fl * MS, lf);
         }
@@ -234,39 +236,75 @@ __global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_
             dev::mbar_expect_tx(w_mbar, bytes);
             dev::tma_bulk_g2s(w_pcm, upcm + (long long)(r + kFusedWarps) * kRound * a.S, bytes, w_mbar);
         }
-        // ---- phase 2: mel + log (+ DCT); lane (f2, q) owns filters q, q+TPF, ... of frame f2. 128-bit loads of the
-        //      magnitudes and of the zero-padded weight list (both on the 4-bin grid), 4 partial sums per filter.
+        // ---- phase 2: mel + log (+ DCT), TPF lanes per frame.
+        //  (i)  the TPF lanes of a frame share every filter: lane q multiplies the 4-bin chunks q, q+TPF, ... of the
+        //       filter's zero-padded weight list with the magnitudes (two 128-bit loads + 4 FMA per chunk) - no
+        //       divergence, no bank conflicts;
+        //  (ii) a transpose-reduce over the TPF lanes leaves the total of filter g*TPF + q in lane q, which takes the log
+        //       and accumulates its share of the DCT; one final butterfly sums the DCT over the TPF lanes.
         {
-            const float *mrow = w_mags + f2 * MS;
+            const float4 *mrow = reinterpret_cast<const float4 *>(w_mags + f2 * MS) + q;
+            const float4 *wl = reinterpret_cast<const float4 *>(s_wlist) + q;
             float cep[16];
 #pragma unroll
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
             float *crow = s_cep + (f0 + f2) * cols;
             const bool live = f0 + f2 < ncomp;
-            for (int b = q; b < a.nb; b += TPF) {
-                const int n = s_flen[b];
-                const float4 *mv = reinterpret_cast<const float4 *>(mrow + s_fstart[b]);
-                const float4 *wv = reinterpret_cast<const float4 *>(s_wlist) + s_woff[b];
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < n; i++) {
-                    const float4 m = mv[i], w = wv[i];
-                    a0 = fmaf(w.x, m.x, a0); a1 = fmaf(w.y, m.y, a1);
-                    a2 = fmaf(w.z, m.z, a2); a3 = fmaf(w.w, m.w, a3);
-                }
-                const float e = dev::mel_log<FAST>((a0 + a1) + (a2 + a3));
-                if (a.dct_len > 0) {
-                    const float4 *row = reinterpret_cast<const float4 *>(s_dct + b * 16);
+            for (int g = 0; g < a.nb; g += TPF) {
+                float p[TPF];
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const float4 d4 = row[c4];
-                        cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
-                        cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
-                        cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
-                        cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
+                for (int k = 0; k < TPF; k++) {
+                    const int b = min(g + k, a.nb - 1); // (a short last group recomputes the last filter; unused)
+                    const int4 fi = s_fidx4[b];         // {first chunk, iterations, weight offset (float4 units), -}
+                    const float4 *mv = mrow + fi.x;
+                    const float4 *wv = wl + fi.z;
+                    float4 m = mv[0], w = wv[0];
+                    float a0 = w.x * m.x, a1 = w.y * m.y, a2 = w.z * m.z, a3 = w.w * m.w;
+#pragma unroll 1
+                    for (int i = 1; i < fi.y; i++) { // most filters need one chunk per lane
+                        m = mv[i * TPF]; w = wv[i * TPF];
+                        a0 = fmaf(w.x, m.x, a0); a1 = fmaf(w.y, m.y, a1);
+                        a2 = fmaf(w.z, m.z, a2); a3 = fmaf(w.w, m.w, a3);
                     }
-                } else if (live)
-                    crow[b] = e;
+                    p[k] = (a0 + a1) + (a2 + a3);
+                }
+                // transpose-reduce: afterwards lane q holds sum over the TPF lanes of p[q]
+                float tot;
+                if (TPF == 8) {
+                    const bool h4 = q & 4;
+                    float r[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float keep = h4 ? p[k + 4] : p[k], send = h4 ? p[k] : p[k + 4];
+                        r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) p[k] = r[k];
+                }
+                {
+                    const bool h2 = q & 2, h1 = q & 1;
+                    const float k0 = h2 ? p[2] : p[0], k1 = h2 ? p[3] : p[1];
+                    const float s0 = h2 ? p[0] : p[2], s1 = h2 ? p[1] : p[3];
+                    const float u0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+                    const float u1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+                    tot = (h1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h1 ? u0 : u1, 1);
+                }
+                const int b = g + q;
+                const float e = dev::mel_log<FAST>(tot);
+                if (b < a.nb) {
+                    if (a.dct_len > 0) {
+                        const float4 *row = reinterpret_cast<const float4 *>(s_dct + b * 16);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const float4 d4 = row[c4];
+                            cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
+                            cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
+                            cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
+                            cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
+                        }
+                    } else if (live)
+                        crow[b] = e;
+                }
             }
             if (a.dct_len > 0) {
                 // sum over the TPF lanes of a frame; lane q then writes the columns c = q (mod TPF)
