@@ -48,51 +48,27 @@ void MelTables::release()
     if (d_dct) cudaFree(d_dct);
     if (d_window) cudaFree(d_window);
     if (d_window2) cudaFree(d_window2);
-    if (d_fidx) cudaFree(d_fidx);
-    if (d_wlist) cudaFree(d_wlist);
-    if (d_dct16) cudaFree(d_dct16);
-    d_fidx = nullptr; d_wlist = nullptr; d_dct16 = nullptr; nwl = 0;
     d_edges = nullptr; d_pairs = nullptr; d_dct = nullptr; d_window = nullptr; d_window2 = nullptr;
     alpha_built = -1.f;
 }
 
-void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st, int tpf)
+void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st)
 {
-    std::vector<int> edges, fidx; std::vector<float> filters, pairs, dct, wlist;
+    std::vector<int> edges; std::vector<float> filters, pairs, dct;
     build_filters(d, alpha, edges, filters);
     for (int i = 0; i + 1 < (int)edges.size(); i++)
         if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     build_mel_pairs(d, edges, filters, pairs);
-    t.tpf = tpf;
-    if (tpf > 0) { // only the fused kernel uses the per-filter lists
-    int max_bin = 0;
-    build_filter_lists(d, edges, filters, tpf, fidx, wlist, max_bin);
-    if (max_bin > kMagRow) throw Error("mel filter too wide for the fused kernel's magnitude rows");
-    if (!t.d_fidx) AFE_CUDA(cudaMalloc(&t.d_fidx, sizeof(int) * fidx.size()));
-    if (t.d_wlist && (int)wlist.size() > t.nwl) { cudaFree(t.d_wlist); t.d_wlist = nullptr; }
-    if (!t.d_wlist) AFE_CUDA(cudaMalloc(&t.d_wlist, sizeof(float) * std::max<size_t>(wlist.size(), 2 * (size_t)d.bins + 36 * (size_t)d.nb)));
-    t.nwl = (int)wlist.size();
-    AFE_CUDA(cudaMemcpyAsync(t.d_fidx, fidx.data(), sizeof(int) * fidx.size(), cudaMemcpyHostToDevice, st));
-    AFE_CUDA(cudaMemcpyAsync(t.d_wlist, wlist.data(), sizeof(float) * wlist.size(), cudaMemcpyHostToDevice, st));
-    }
     if (!t.d_edges) AFE_CUDA(cudaMalloc(&t.d_edges, sizeof(int) * (d.nb + 2)));
     if (!t.d_pairs) AFE_CUDA(cudaMalloc(&t.d_pairs, sizeof(float) * 2 * d.bins));
     // pageable source + stream-ordered copy: cudaMemcpyAsync from pageable memory stages synchronously, safe with locals
     AFE_CUDA(cudaMemcpyAsync(t.d_edges, edges.data(), sizeof(int) * (d.nb + 2), cudaMemcpyHostToDevice, st));
     AFE_CUDA(cudaMemcpyAsync(t.d_pairs, pairs.data(), sizeof(float) * 2 * d.bins, cudaMemcpyHostToDevice, st));
-    std::vector<float> dct16;
     if (d.C > 0 && !t.d_dct) {
         build_dct(d, dct);
         AFE_CUDA(cudaMalloc(&t.d_dct, sizeof(float) * dct.size()));
         AFE_CUDA(cudaMemcpyAsync(t.d_dct, dct.data(), sizeof(float) * dct.size(), cudaMemcpyHostToDevice, st));
-        if (d.dct_len <= 16) {
-            dct16.assign((size_t)d.nb * 16, 0.f);
-            for (int k = 0; k < d.nb; k++)
-                for (int j = 0; j < d.dct_len; j++) dct16[(size_t)k * 16 + j] = dct[(size_t)k * d.dct_len + j];
-            AFE_CUDA(cudaMalloc(&t.d_dct16, sizeof(float) * dct16.size()));
-            AFE_CUDA(cudaMemcpyAsync(t.d_dct16, dct16.data(), sizeof(float) * dct16.size(), cudaMemcpyHostToDevice, st));
-        }
     }
     AFE_CUDA(cudaStreamSynchronize(st));
     t.alpha_built = alpha;
@@ -189,8 +165,9 @@ struct afe_batch {
     double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
-    int shape_warps = 8, shape_round = 4;   // kernel shape, see afe_fused.cuh (AFE_FUSED_SHAPE=4x8 selects the other one)
     FusedSmem L{};
+    MelConst mc;
+    float mc_alpha = -1.f;
     int last_launches = 0;
     // host staging for run_host
     int16_t *d_pcm_stage = nullptr; float *d_out_stage = nullptr;
@@ -212,31 +189,50 @@ struct afe_batch {
 
 static void check_fused_support(const Derived &d)
 {
-    const int kFusedThreads = 128; // the smaller of the two kernel shapes bounds the output width
     if (d.N2 != 512 && d.N2 != 256)
         throw Error("fused batch path supports 256/512-point FFTs (window_size 129..512); use the streaming object");
     if (d.S % 2) throw Error("fused batch path needs an even shift");
     if (d.dct_len > 16) throw Error("fused batch path supports ceps_len + c0 <= 16");
     if (d.width > kFusedThreads) throw Error("fused batch path supports output width <= 128");
-    if (d.nb + 2 > 256) throw Error("fused batch path supports num_banks <= 254");
+    if (d.nb > kMaxBanks) throw Error("fused batch path supports num_banks <= 64");
 }
 
 template <int N2> static FusedSmem layout_for(const afe_batch *b)
 {
     const Derived &d = b->d;
-    // wlist: <= 2 entries per bin (rising + falling side) plus <= 6 floats of alignment padding per filter
-    return fused_smem_layout<N2>(b->shape_warps, b->shape_round, d.S, d.nb, 2 * d.bins + 36 * d.nb, d.C > 0 ? d.dct_len : 0, d.cols, b->tc_max, b->nout_max,
-                                 d.l2, d.width / d.cols);
+    return fused_smem_layout<N2>(d.S, d.cols, b->tc_max, b->nout_max, d.l2, d.width / d.cols);
 }
 
-template <int N2, int NZ, int WARPS, int ROUND>
-static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+// Mel weights + DCT matrix as a by-value kernel parameter (constant bank). Per filter b: bins [edges[b], edges[b+2]) with
+// weights filters[b%2][bin] — the per-filter form of the reference's two-running-sums sweep (mfcccpu.cpp:192-220).
+static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
+{
+    std::vector<int> edges; std::vector<float> filters, dct;
+    build_filters(d, alpha, edges, filters);
+    for (int i = 0; i + 1 < (int)edges.size(); i++)
+        if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
+    if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
+    memset(&mc, 0, sizeof mc);
+    int off = 0;
+    for (int b = 0; b < d.nb; b++) {
+        const int j0 = edges[b], n = edges[b + 2] - edges[b];
+        if (off + n > kMaxWl) throw Error("mel weight list exceeds the kernel-parameter budget");
+        mc.fstart[b] = (short)j0; mc.flen[b] = (short)n; mc.woff[b] = (short)off;
+        for (int j = 0; j < n; j++) mc.wl[off + j] = filters[(size_t)(b % 2) * d.N2 + j0 + j];
+        off += n;
+    }
+    if (d.C > 0) {
+        build_dct(d, dct);
+        memcpy(mc.dct, dct.data(), sizeof(float) * dct.size());
+    }
+}
+
+template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
 {
     const Derived &d = b->d;
     FusedArgs a{};
     a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles;
     a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.fidx = b->mel.d_fidx; a.wlist = b->mel.d_wlist; a.nwl = b->mel.nwl; a.dct = b->mel.d_dct16;
     a.partials = want_stats ? b->d_partials : nullptr;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
@@ -245,18 +241,17 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     if (!want_stats) a.stats_rows_mode = 0;
     else if (!d.p.norm_after_dyn) a.stats_rows_mode = 2;
     else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
+    a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     a.tc_max = b->tc_max;
     float den1 = 0, den2 = 0;
     for (int l = 1; l <= d.l1; l++) den1 += l * l;   // float accumulation like deltacpu.cpp:26
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
-    if (a.nwl > 2 * d.bins + 36 * d.nb) throw Error("mel weight list exceeds its shared-memory budget");
-    a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, ROUND> : k_fused_mfcc<N2, NZ, false, WARPS, ROUND>;
+    auto kern = fast ? k_fused_mfcc<N2, NZ, true> : k_fused_mfcc<N2, NZ, false>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    kern<<<b->n_tiles, 32 * WARPS, b->L.total, b->stream>>>(a, b->L);
+    kern<<<b->n_tiles, kFusedThreads, b->L.total, b->stream>>>(a, b->L, b->mc);
     AFE_CUDA(cudaGetLastError());
     count_launch();
     b->last_launches++;
@@ -266,23 +261,13 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
 {
     if (!b->window_set) throw Error("set_window must be called before running");
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
-    const int tpf = 32 / b->shape_round;
-    if (b->mel.alpha_built != b->alpha || b->mel.tpf != tpf) upload_mel_tables(b->d, b->alpha, b->mel, b->stream, tpf);
+    if (b->mc_alpha != b->alpha) { build_mel_const(b->d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
     b->last_launches = 0;
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->shape_warps == 8 ? 1 : 0);
-    switch (key) {
-    case 0: launch_fused<512, 13, 4, 8>(b, d_pcm, d_out, want_stats); break;
-    case 1: launch_fused<512, 13, 8, 4>(b, d_pcm, d_out, want_stats); break;
-    case 2: launch_fused<512, 16, 4, 8>(b, d_pcm, d_out, want_stats); break;
-    case 3: launch_fused<512, 16, 8, 4>(b, d_pcm, d_out, want_stats); break;
-    case 4: launch_fused<256, 13, 4, 8>(b, d_pcm, d_out, want_stats); break;
-    case 5: launch_fused<256, 13, 8, 4>(b, d_pcm, d_out, want_stats); break;
-    case 6: launch_fused<256, 16, 4, 8>(b, d_pcm, d_out, want_stats); break;
-    default: launch_fused<256, 16, 8, 4>(b, d_pcm, d_out, want_stats); break;
-    }
+    if (b->d.N2 == 512) pruned ? launch_fused<512, 13>(b, d_pcm, d_out, want_stats) : launch_fused<512, 16>(b, d_pcm, d_out, want_stats);
+    else pruned ? launch_fused<256, 13>(b, d_pcm, d_out, want_stats) : launch_fused<256, 16>(b, d_pcm, d_out, want_stats);
 }
 
 static void run_reduce(afe_batch *b)
@@ -376,14 +361,11 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         DeviceGuard g(b->device);
         b->free_plan();
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
-        const char *env_shape = getenv("AFE_FUSED_SHAPE");
-        if (env_shape && !strcmp(env_shape, "4x8")) { b->shape_warps = 4; b->shape_round = 8; }
-        else if (env_shape && !strcmp(env_shape, "8x4")) { b->shape_warps = 8; b->shape_round = 4; }
-        const int kRound = b->shape_round;
+        // tile geometry: the cepstra tile holds up to 352 frames (<= 4.6 K floats of shared memory)
         const char *env_tc = getenv("AFE_TILE_FRAMES");
-        int tc = env_tc ? atoi(env_tc) : 264;
-        tc = std::min(tc, (4096 / d.cols) / kRound * kRound);
-        tc = std::max(tc, kRound * ((2 * d.D + 1 + kRound - 1) / kRound + 1));
+        int tc = env_tc ? atoi(env_tc) : 352;
+        tc = std::min(tc, (4608 / d.cols) / kRoundFrames * kRoundFrames);
+        tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
         b->tc_max = tc; b->nout_max = tc - 2 * d.D;
         b->n_utts = n_utts;
         b->sample_off.assign(off, off + n_utts);
@@ -404,7 +386,17 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             const int T = afe_estimated_window_count((int)n, d.W, d.S);
             if (T <= 2 * d.D || T < 1) throw Error("Can't process data, window count is too small"); // segmentercpu.cpp:65-66
             b->frame_off[u + 1] = b->frame_off[u] + T;
-            const int ntile = (T + b->nout_max - 1) / b->nout_max;
+            // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
+            int ntile = (T + b->nout_max - 1) / b->nout_max, best_cost = 1 << 30;
+            for (int cand = ntile; cand <= ntile + 3; cand++) {
+                const int no = (T + cand - 1) / cand;
+                int cost = 0;
+                for (int t0 = 0; t0 < T; t0 += no) {
+                    const int c0 = std::max(0, t0 - d.D), c1 = std::min(T, t0 + std::min(no, T - t0) + d.D);
+                    cost += (c1 - c0 + kRoundFrames - 1) / kRoundFrames;
+                }
+                if (cost < best_cost) { best_cost = cost; ntile = cand; }
+            }
             const int nout = (T + ntile - 1) / ntile;
             if (!corpus) tile_begin.push_back((int)tiles.size());
             for (int t0 = 0; t0 < T; t0 += nout) {

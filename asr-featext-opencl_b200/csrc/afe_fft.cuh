@@ -120,11 +120,25 @@ template <int NZ> __device__ __forceinline__ void fft16_in(float2 (&x)[16])
         fft16(x);
 }
 
-// twiddles of the stage A -> stage B exchange, per lane, kept in registers: exp(-2 pi i lane*k1 / M), k1 = 0..15
-template <int N2> __device__ __forceinline__ void load_twa(float2 (&twa)[16], const float2 *__restrict__ tw_a, int lf)
+// Per-lane constants kept in registers for the whole kernel (shared memory bandwidth is the scarce resource here,
+// profiles/r01_v4b_8x4_k_fused_summary.txt): window pairs, exchange twiddles, split twiddles.
+template <int N2, int NZ> struct LaneConsts {
+    float2 win[NZ]; // (w[2n], w[2n+1]) for n = R*n1 + lane, n1 < NZ (zero beyond)
+    float2 twa[16]; // exp(-2 pi i lane*k1 / M)
+    float2 twp[8];  // exp(-2 pi i (lane + R*m) / N2)
+};
+
+template <int N2, int NZ>
+__device__ __forceinline__ void load_lane_consts(LaneConsts<N2, NZ> &lc, const float2 *__restrict__ window2,
+                                                 const float2 *__restrict__ tw_a, const float2 *__restrict__ tw_p, int lf)
 {
+    using C = FftCfg<N2>;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1++) twa[k1] = tw_a[lf * 16 + k1];
+    for (int n1 = 0; n1 < NZ; n1++) lc.win[n1] = window2[C::R * n1 + lf];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) lc.twa[k1] = tw_a[lf * 16 + k1];
+#pragma unroll
+    for (int m = 0; m < 8; m++) lc.twp[m] = tw_p[lf + C::R * m];
 }
 
 template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
@@ -140,13 +154,12 @@ template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
 // One frame per R-lane group; ALL 32 lanes of the warp must call (uses __syncwarp). Branch free.
 //   words    : the frame's PCM as 32-bit words (2 int16 each), readable for NZ*R words; samples beyond W meet a 0 window
 //   NZ       : leading n1 slots that can be non-zero (13 when W <= 26*R, else 16)
-//   win2     : (w[2n], w[2n+1]) for n < M, zero padded (shared memory)
-//   twp      : exp(-2 pi i k / N2), k < M/2 (shared memory)
+//   lc       : this lane's window pairs and twiddles (registers)
 //   scratch  : this frame's exchange tile, FftCfg::SCR float2
 //   mag_out  : BINS floats (always written; padding frames point at a row nobody reads)
 template <int N2, int NZ, bool FAST>
-__device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const float2 *win2, const float2 *twp,
-                                              const float2 (&twa)[16], float2 *scratch, float *mag_out, int lf)
+__device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneConsts<N2, NZ> &lc, float2 *scratch,
+                                              float *mag_out, int lf)
 {
     using C = FftCfg<N2>;
     constexpr int M = C::M, R = C::R, RS = C::RS;
@@ -155,7 +168,7 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const float
     for (int n1 = 0; n1 < 16; n1++) {
         if (n1 < NZ) {
             const uint32_t w = words[R * n1 + lf];
-            const float2 wn = win2[R * n1 + lf];
+            const float2 wn = lc.win[n1];
             const float lo = (float)(int)(short)(w & 0xffffu);
             const float hi = (float)((int)w >> 16);
             x[n1] = make_float2(lo * wn.x, hi * wn.y);
@@ -167,7 +180,7 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const float
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
         float2 v = x[pos16(k1)];
-        if (k1 > 0) v = cmul(v, twa[k1]);
+        if (k1 > 0) v = cmul(v, lc.twa[k1]);
         scratch[k1 * RS + lf] = v;
     }
     __syncwarp();
@@ -201,12 +214,11 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const float
     const float scale = 0.5f / (float)N2; // |2X| * 0.5/N2 == |X|/N2 exactly (powers of two)
     const float2 *fwd = scratch + lf, *rev = scratch + (M - lf);
     float *mf = mag_out + lf, *mr = mag_out + (M - lf);
-    const float2 *tw = twp + lf;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         const float2 a = fwd[R * m];
         const float2 b = rev[-R * m];
-        const float2 w = tw[R * m];
+        const float2 w = lc.twp[m];
         const float sr = a.x + b.x, si = a.y - b.y; // a + conj(b)
         const float dr = a.x - b.x, di = a.y + b.y; // a - conj(b)
         const float pr = dr * w.x - di * w.y, pi = dr * w.y + di * w.x;

@@ -1,19 +1,23 @@
 // K1: the fused hot-path kernel.  int16 PCM -> window -> real FFT -> |X|/N2 -> mel+log -> DCT -> delta/delta-delta
 // -> feature rows (+ per-tile column statistics): one HBM read of PCM and one HBM write of features per frame.
 //
-// Work item = (utterance, tile of `nout` output frames). A CTA computes the cepstra of its tile plus a halo of
-// D = l1+l2 frames on each side (clamped at the utterance edges, where the reference replicates the edge frame,
-// mfcccpu.cpp:243-254). Inside the CTA every WARP IS AUTONOMOUS: it owns rounds of 8 consecutive frames and runs
-//   stage 0  one cp.async.bulk (TMA, SASS UBLKCP) of the round's PCM into the warp's own staging buffer, completion on
-//            the warp's own mbarrier; the next round's copy is issued as soon as the FFTs of this round are done
-//   phase 1  8/FPW calls of the in-register FFT + magnitude (afe_fft.cuh)            -> warp-private mags[8][260]
-//   phase 2  mel + log + DCT with 4 lanes per frame, each lane owning the filters b = q (mod 4) (summation order per
-//            filter = the reference's ascending-bin order, mfcccpu.cpp:192-220)       -> cep[tile][cols] (CTA shared)
-// with only __syncwarp between the steps, so warps of the resident CTAs interleave freely and no warp ever waits
-// at a CTA barrier inside the loop (v1 lost 39 % of its issue slots there, profiles/r01_v1_k_fused_summary.txt).
-// One __syncthreads later:
+// Work item = (utterance, tile of `nout` output frames). A CTA (4 warps) computes the cepstra of its tile plus a halo
+// of D = l1+l2 frames on each side (clamped at the utterance edges, where the reference replicates the edge frame,
+// mfcccpu.cpp:243-254) in rounds of 32 frames:
+//   stage 0  each warp stages the PCM of ITS 8 frames with one cp.async.bulk (TMA, SASS UBLKCP) into its own buffer,
+//            completion on its own mbarrier; the next round's copy is issued as soon as this round's FFTs are done
+//   phase 1  each warp: 8/FPW calls of the in-register FFT + magnitude (afe_fft.cuh) -> mags[32][257] (CTA shared);
+//            frame f lives in row (f>>1) + 16*(f&1): the two adjacent frames of one call land 16 banks apart AND
+//            phase 2's "lane = frame" reads of one bin hit 32 different banks
+//   phase 2  mel + log + DCT, ONE THREAD PER FRAME, warp w owning the filters b = w (mod 4). The triangular weights and
+//            the DCT matrix are kernel parameters, i.e. constant-bank operands: they cost no shared-memory bandwidth,
+//            which is what bounds this kernel (v3/v4 re-loaded weights per lane: 116 of 245 smem wavefronts per frame,
+//            profiles/r01_v3_k_fused_summary.txt). Accumulation per filter runs in the reference's ascending-bin order
+//            (mfcccpu.cpp:192-220). Per-warp partial cepstra are summed in a fixed order -> cep[tile][cols].
 //   phase 3  delta on the extended axis -> smem, then rows [static | delta | delta-delta] are written coalesced;
 //            column sums / sums of squares (double) / min / max of the tile go to a per-tile partial record.
+// Two CTA barriers per 32 frames; both phases keep all four warps equally busy (v1 serialised phase 2 on one warp and
+// lost 39 % of its issue slots at the barrier, profiles/r01_v1_k_fused_summary.txt).
 // Replaces, for whole utterances: segmenter.cl, AppleFFT fft0, mfcc.cl kernelTranspose+kernelFilter, DCT.cl,
 // delta.cl and norm.cl:kernelSum.
 #pragma once
@@ -33,16 +37,26 @@ struct Tile {
     int group;           // statistics group (utterance index, or 0 for corpus scope)
 };
 
+constexpr int kMaxBanks = 64;
+constexpr int kMaxWl = 2 * 257 + 2;   // weights: every bin feeds one rising and one falling side
+constexpr int kMaxDct = kMaxBanks * 16;
+
+// Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only.
+struct MelConst {
+    float wl[kMaxWl];            // concatenated per-filter weights: filter b = wl[woff[b] .. woff[b]+flen[b])
+    float dct[kMaxDct];          // [nb][dct_len]
+    short fstart[kMaxBanks];     // first bin of filter b  (= edges[b])
+    short flen[kMaxBanks];       // bins of filter b       (= edges[b+2]-edges[b])
+    short woff[kMaxBanks];
+};
+
 struct FusedArgs {
     const int16_t *pcm;
     float *out;
     const Tile *tiles;
     const float2 *window2, *tw_a, *tw_p;
-    const int *fidx;     // [3][nb]: per filter first bin (multiple of 4), float4 chunks, offset into wlist (float4 units)
-    const float *wlist;  // concatenated triangular weights, filter by filter, zero padded to the float4 grid
-    const float *dct;    // [nb][16] DCT rows zero padded to 16 columns
     double *partials;    // [ntiles][width][4] or nullptr
-    int W, S, nb, dct_len, cols, width, l1, l2, nstreams, nwl;
+    int W, S, nb, dct_len, cols, width, l1, l2, nstreams;
     int q1;              // reproduce the single-block flush quirk
     int use_tma;
     int stats_rows_mode; // 0: no stats, 1: rows < T-D, 2: all rows
@@ -51,52 +65,42 @@ struct FusedArgs {
     float rden1, rden2;  // 1 / (2*sum(l^2))
 };
 
-// Kernel shape: WARPS warps per CTA, each owning rounds of ROUND frames; phase 2 runs 32/ROUND lanes per frame.
-//   <4, 8>: 4 lanes per frame in phase 2 (cheapest mel), 16 KB of shared memory per warp
-//   <8, 4>: 8 lanes per frame, 10.6 KB per warp -> twice the resident warps per SM
-// Magnitude row stride: 272 floats = 68 16-byte chunks. 272 = 16 (mod 32): the two rows written by one FFT call (adjacent
-// frames) land 16 banks apart, and 68 = 4 (mod 8): in phase 2 the TPF lanes of a frame read TPF consecutive chunks and
-// the next frame's lanes the chunks 4 further (mod 8), so a quarter warp always covers 8 distinct chunk groups.
-// Columns M+1..271 are zero (weights there are zero padding; keeps 0*garbage from making NaNs).
-__host__ __device__ constexpr int mag_stride(int) { return 272; }
+constexpr int kFusedWarps = 4;
+constexpr int kFusedThreads = 32 * kFusedWarps;
+constexpr int kRoundFrames = 32;                      // frames per CTA round
+constexpr int kWarpFrames = kRoundFrames / kFusedWarps; // frames per warp and round
 
 struct FusedSmem {
-    int off_mbar, off_win, off_twp, off_fidx, off_wlist, off_dct, off_warp, warp_bytes, w_pcm, w_scratch, w_mags,
-        pcm_bytes, off_dd, off_red, off_cep, total;
+    int off_mbar, off_mags, off_part, off_warp, warp_bytes, w_pcm, w_scratch, pcm_bytes, off_dhat, off_dd, off_red,
+        off_cep, total;
 };
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int N2>
-FusedSmem fused_smem_layout(int kFusedWarps, int kRound, int S, int nb, int nwl, int dct_len, int cols, int tc_max,
-                            int nout_max, int l2, int nstreams)
+FusedSmem fused_smem_layout(int S, int cols, int tc_max, int nout_max, int l2, int nstreams)
 {
-    const int kFusedThreads = 32 * kFusedWarps, kMagStride = mag_stride(kRound);
     using C = dev::FftCfg<N2>;
     FusedSmem L;
     int o = 0;
-    L.off_mbar = o; o += align_up(kFusedWarps * 8, 16); // one mbarrier per warp, never aliased
-    L.off_win = o; o += align_up(C::M * 8, 16);
-    L.off_twp = o; o += align_up(C::M / 2 * 8, 16);
-    L.off_fidx = o; o += nb * 16;
-    L.off_wlist = o; o += align_up(nwl * 4, 16);
-    L.off_dct = o; o += align_up((dct_len > 0 ? nb * 16 : 1) * 4, 16);
-    // per warp: [pcm | scratch | mags]
-    int w = 0;
-    L.pcm_bytes = align_up(((kRound - 1) * S + N2) * 2, 16) + 16;
+    L.off_mbar = o; o += align_up(kFusedWarps * 8, 16);           // one mbarrier per warp, never aliased
+    L.off_mags = o; o += align_up(kRoundFrames * C::BINS * 4, 16); // [32][M+1]
+    L.off_part = o; o += kFusedWarps * 4 * kRoundFrames * 16;      // float4 [warp][c4][frame] partial cepstra
+    int w = 0;                                                     // per warp: [pcm | scratch]
+    L.pcm_bytes = align_up(((kWarpFrames - 1) * S + N2) * 2, 16) + 16;
     L.w_pcm = w; w += L.pcm_bytes;
     L.w_scratch = w; w += align_up(C::FPW * C::SCR * 8, 16);
-    L.w_mags = w; w += align_up(kRound * kMagStride * 4, 16);
     L.warp_bytes = align_up(w, 128);
-    // phase 3 reuses the per-warp area: [delta rows | delta-delta rows | reduction scratch]
+    o = align_up(o, 128);
+    L.off_warp = o; o += kFusedWarps * L.warp_bytes;
+    // phase 3 reuses everything between off_mags and off_cep: [delta rows | delta-delta rows | reduction scratch]
     const int dhat = nstreams >= 2 ? align_up((nout_max + 2 * l2) * cols * 4, 16) : 0;
     const int dd = nstreams >= 3 ? align_up(nout_max * cols * 4, 16) : 0;
-    const int phase3 = dhat + dd + kFusedThreads * 4 * 8;
-    o = align_up(o, 128);
-    L.off_warp = o;
-    L.off_dd = o + dhat;
-    L.off_red = o + dhat + dd;
-    o += align_up(kFusedWarps * L.warp_bytes > phase3 ? kFusedWarps * L.warp_bytes : phase3, 128);
+    L.off_dhat = L.off_mags;
+    L.off_dd = L.off_dhat + dhat;
+    L.off_red = L.off_dd + dd;
+    const int phase3_end = L.off_red + kFusedThreads * 4 * 8;
+    if (phase3_end > o) o = align_up(phase3_end, 128);
     L.off_cep = o; o += align_up(tc_max * cols * 4, 16);
     L.total = o;
     return L;
@@ -143,189 +147,137 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 } // namespace dev
 
-template <int N2, int NZ, bool FAST, int kFusedWarps, int kRound>
-__global__ void __launch_bounds__(32 * kFusedWarps, kFusedWarps == 4 ? 3 : 2) k_fused_mfcc(const FusedArgs a, const FusedSmem L)
+template <int N2, int NZ, bool FAST>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
     using C = dev::FftCfg<N2>;
-    constexpr int kFusedThreads = 32 * kFusedWarps;
-    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, M = C::M, MS = mag_stride(kRound);
-    constexpr int ITERS = kRound / FPW; // FFT calls per round
-    constexpr int TPF = 32 / kRound;    // phase-2 lanes per frame
-    static_assert(kRound % FPW == 0 && (TPF == 4 || TPF == 8), "unsupported kernel shape");
+    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, BINS = C::BINS;
     extern __shared__ __align__(128) unsigned char smem[];
-    float2 *s_win = reinterpret_cast<float2 *>(smem + L.off_win);
-    float2 *s_twp = reinterpret_cast<float2 *>(smem + L.off_twp);
-    int4 *s_fidx4 = reinterpret_cast<int4 *>(smem + L.off_fidx);
-    float *s_wlist = reinterpret_cast<float *>(smem + L.off_wlist);
-    float *s_dct = reinterpret_cast<float *>(smem + L.off_dct);
+    float *s_mags = reinterpret_cast<float *>(smem + L.off_mags);
+    float4 *s_part = reinterpret_cast<float4 *>(smem + L.off_part);
     float *s_cep = reinterpret_cast<float *>(smem + L.off_cep);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp-uniform for the compiler: constant-bank indexing
     const int lf = lane % R, fw = lane / R;
     unsigned char *wbase = smem + L.off_warp + warp * L.warp_bytes;
     uint64_t *w_mbar = reinterpret_cast<uint64_t *>(smem + L.off_mbar) + warp;
     unsigned char *w_pcm = wbase + L.w_pcm;
     float2 *w_scratch = reinterpret_cast<float2 *>(wbase + L.w_scratch);
-    float *w_mags = reinterpret_cast<float *>(wbase + L.w_mags);
 
     const Tile tl = a.tiles[blockIdx.x];
     const int D = a.l1 + a.l2, cols = a.cols;
     const int c0f = max(0, tl.t0 - D), c1f = min(tl.T, tl.t0 + tl.nout + D);
     const int ncomp = c1f - c0f;
-    const int nrounds = (ncomp + kRound - 1) / kRound;
-    const int16_t *upcm = a.pcm + tl.pcm_off + (long long)c0f * a.S;
-
-    auto round_bytes = [&](int r) {
-        return (uint32_t)((((min(kRound, ncomp - r * kRound) - 1) * a.S + a.W) * 2 + 15) & ~15);
+    const int nrounds = (ncomp + kRoundFrames - 1) / kRoundFrames;
+    // this warp's frames of round r: [r*32 + warp*8, +8)
+    const int16_t *wpcm = a.pcm + tl.pcm_off + (long long)(c0f + warp * kWarpFrames) * a.S;
+    auto warp_frames = [&](int r) { return min(kWarpFrames, ncomp - r * kRoundFrames - warp * kWarpFrames); };
+    auto issue_tma = [&](int r) { // lane 0 only; nothing to copy when the warp has no frame in round r
+        const int nf = warp_frames(r);
+        if (nf <= 0) return;
+        const uint32_t bytes = (uint32_t)((((nf - 1) * a.S + a.W) * 2 + 15) & ~15);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        dev::mbar_expect_tx(w_mbar, bytes);
+        dev::tma_bulk_g2s(w_pcm, wpcm + (long long)r * kRoundFrames * a.S, bytes, w_mbar);
     };
-    // issue the first copy before anything else so that it overlaps the table loads
     if (a.use_tma && lane == 0) {
         dev::mbar_init(w_mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (warp < nrounds) {
-            const uint32_t bytes = round_bytes(warp);
-            dev::mbar_expect_tx(w_mbar, bytes);
-            dev::tma_bulk_g2s(w_pcm, upcm + (long long)warp * kRound * a.S, bytes, w_mbar);
-        }
+        issue_tma(0); // overlaps the constant loads below
     }
-    for (int i = tid; i < M; i += kFusedThreads) s_win[i] = a.window2[i];
-    for (int i = tid; i < M / 2; i += kFusedThreads) s_twp[i] = a.tw_p[i];
-    for (int i = tid; i < a.nb; i += kFusedThreads) s_fidx4[i] = reinterpret_cast<const int4 *>(a.fidx)[i];
-    for (int i = tid; i < a.nwl; i += kFusedThreads) s_wlist[i] = a.wlist[i];
-    if (a.dct_len > 0)
-        for (int i = tid; i < a.nb * 16; i += kFusedThreads) s_dct[i] = a.dct[i];
-    float2 twa[16];
-    dev::load_twa<N2>(twa, a.tw_a, lf);
-    // the 128-bit mel loads may touch the 3 pad floats behind bin M of a magnitude row (with zero weights): keep them finite
-    for (int i = lane; i < kRound * (MS - M - 1); i += 32) w_mags[(i / (MS - M - 1)) * MS + M + 1 + i % (MS - M - 1)] = 0.f;
+    dev::LaneConsts<N2, NZ> lc;
+    dev::load_lane_consts<N2, NZ>(lc, a.window2, a.tw_a, a.tw_p, lf);
     __syncthreads();
 
-    const int f2 = lane / TPF, q = lane % TPF; // phase 2: frame within the round, lane within the frame
     uint32_t parity = 0;
-    for (int r = warp; r < nrounds; r += kFusedWarps) {
-        const int f0 = r * kRound;
-        if (a.use_tma) {
-            dev::mbar_wait(w_mbar, parity);
-            parity ^= 1;
-        } else {
-            // plain staging (any alignment): the round's samples, 32-bit words when the source allows
-            const int16_t *src = upcm + (long long)f0 * a.S;
-            const int n = (min(kRound, ncomp - f0) - 1) * a.S + a.W;
-            int16_t *dst = reinterpret_cast<int16_t *>(w_pcm);
-            if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-                const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
-                uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-                for (int i = lane; i < n / 2; i += 32) d32[i] = __ldg(s32 + i);
-                if ((n & 1) && lane == 0) dst[n - 1] = src[n - 1];
-            } else
-                for (int i = lane; i < n; i += 32) dst[i] = src[i];
-            __syncwarp();
-        }
-        // ---- phase 1: FFT + magnitude. Call `it` transforms the adjacent frames it*FPW + fw of the round: their PCM
-        //      (S/2 words apart) and their magnitude rows (272 floats apart) start 16 / 8 banks apart
+    for (int r = 0; r < nrounds; r++) {
+        const int f0 = r * kRoundFrames;            // first frame of the round (tile-local)
+        const int nfr = min(kRoundFrames, ncomp - f0); // live frames of the round
+        const int nfw = warp_frames(r);              // live frames of this warp
+        // ---- stage 0 + phase 1 (skipped by warps without a live frame in a short last round)
+        if (nfw > 0) {
+            if (a.use_tma) {
+                dev::mbar_wait(w_mbar, parity);
+                parity ^= 1;
+            } else {
+                // plain staging (any alignment): the warp's samples, 32-bit words when the source allows
+                const int16_t *src = wpcm + (long long)f0 * a.S;
+                const int n = (nfw - 1) * a.S + a.W;
+                int16_t *dst = reinterpret_cast<int16_t *>(w_pcm);
+                if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+                    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
+                    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+                    for (int i = lane; i < n / 2; i += 32) d32[i] = __ldg(s32 + i);
+                    if ((n & 1) && lane == 0) dst[n - 1] = src[n - 1];
+                } else
+                    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+                __syncwarp();
+            }
 #pragma unroll 1
-        for (int it = 0; it < ITERS; it++) {
-            const int fl = it * FPW + fw;
-            const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
-            dev::fft_frame_mag<N2, NZ, true>(words, s_win, s_twp, twa, w_scratch + fw * SCR, w_mags + fl * MS, lf);
+            for (int it = 0; it * FPW < nfw; it++) {
+                const int fl = it * FPW + fw;                    // frame within the warp's 8 (adjacent frames per call)
+                const int fr = warp * kWarpFrames + fl;          // frame within the round
+                const int row = (fr >> 1) + 16 * (fr & 1);       // magnitude row (see header)
+                const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
+                dev::fft_frame_mag<N2, NZ, true>(words, lc, w_scratch + fw * SCR, s_mags + row * BINS, lf);
+            }
+            // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
+            if (a.use_tma && lane == 0 && r + 1 < nrounds) issue_tma(r + 1);
         }
-        // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
-        if (a.use_tma && lane == 0 && r + kFusedWarps < nrounds) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bytes = round_bytes(r + kFusedWarps);
-            dev::mbar_expect_tx(w_mbar, bytes);
-            dev::tma_bulk_g2s(w_pcm, upcm + (long long)(r + kFusedWarps) * kRound * a.S, bytes, w_mbar);
-        }
-        // ---- phase 2: mel + log (+ DCT), TPF lanes per frame.
-        //  (i)  the TPF lanes of a frame share every filter: lane q multiplies the 4-bin chunks q, q+TPF, ... of the
-        //       filter's zero-padded weight list with the magnitudes (two 128-bit loads + 4 FMA per chunk) - no
-        //       divergence, no bank conflicts;
-        //  (ii) a transpose-reduce over the TPF lanes leaves the total of filter g*TPF + q in lane q, which takes the log
-        //       and accumulates its share of the DCT; one final butterfly sums the DCT over the TPF lanes.
-        {
-            const float4 *mrow = reinterpret_cast<const float4 *>(w_mags + f2 * MS) + q;
-            const float4 *wl = reinterpret_cast<const float4 *>(s_wlist) + q;
+        __syncthreads(); // A: all magnitudes of the round are in shared memory
+
+        // ---- phase 2: lane = frame of the round, warp = filter class
+        if (lane < nfr) {
+            const float *mrow = s_mags + ((lane >> 1) + 16 * (lane & 1)) * BINS;
             float cep[16];
 #pragma unroll
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
-            float *crow = s_cep + (f0 + f2) * cols;
-            const bool live = f0 + f2 < ncomp;
-            for (int g = 0; g < a.nb; g += TPF) {
-                float p[TPF];
+            for (int b = warp; b < a.nb; b += kFusedWarps) {
+                const int j0 = mc.fstart[b], n = mc.flen[b];
+                const float *wv = mc.wl + mc.woff[b];
+                const float *mv = mrow + j0;
+                float acc = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < n; i++) acc = fmaf(wv[i], mv[i], acc); // ascending bins, like the reference sweep
+                const float e = dev::mel_log<FAST>(acc);
+                if (a.dct_len > 0) {
+                    const float *drow = mc.dct + b * a.dct_len;
 #pragma unroll
-                for (int k = 0; k < TPF; k++) {
-                    const int b = min(g + k, a.nb - 1); // (a short last group recomputes the last filter; unused)
-                    const int4 fi = s_fidx4[b];         // {first chunk, iterations, weight offset (float4 units), -}
-                    const float4 *mv = mrow + fi.x;
-                    const float4 *wv = wl + fi.z;
-                    float4 m = mv[0], w = wv[0];
-                    float a0 = w.x * m.x, a1 = w.y * m.y, a2 = w.z * m.z, a3 = w.w * m.w;
-#pragma unroll 1
-                    for (int i = 1; i < fi.y; i++) { // most filters need one chunk per lane
-                        m = mv[i * TPF]; w = wv[i * TPF];
-                        a0 = fmaf(w.x, m.x, a0); a1 = fmaf(w.y, m.y, a1);
-                        a2 = fmaf(w.z, m.z, a2); a3 = fmaf(w.w, m.w, a3);
-                    }
-                    p[k] = (a0 + a1) + (a2 + a3);
-                }
-                // transpose-reduce: afterwards lane q holds sum over the TPF lanes of p[q]
-                float tot;
-                if (TPF == 8) {
-                    const bool h4 = q & 4;
-                    float r[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float keep = h4 ? p[k + 4] : p[k], send = h4 ? p[k] : p[k + 4];
-                        r[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) p[k] = r[k];
-                }
-                {
-                    const bool h2 = q & 2, h1 = q & 1;
-                    const float k0 = h2 ? p[2] : p[0], k1 = h2 ? p[3] : p[1];
-                    const float s0 = h2 ? p[0] : p[2], s1 = h2 ? p[1] : p[3];
-                    const float u0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-                    const float u1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-                    tot = (h1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h1 ? u0 : u1, 1);
-                }
-                const int b = g + q;
-                const float e = dev::mel_log<FAST>(tot);
-                if (b < a.nb) {
-                    if (a.dct_len > 0) {
-                        const float4 *row = reinterpret_cast<const float4 *>(s_dct + b * 16);
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            const float4 d4 = row[c4];
-                            cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
-                            cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
-                            cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
-                            cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
-                        }
-                    } else if (live)
-                        crow[b] = e;
-                }
+                    for (int c = 0; c < 16; c++)
+                        if (c < a.dct_len) cep[c] = fmaf(e, drow[c], cep[c]);
+                } else
+                    s_cep[(f0 + lane) * cols + b] = e;
             }
             if (a.dct_len > 0) {
-                // sum over the TPF lanes of a frame; lane q then writes the columns c = q (mod TPF)
 #pragma unroll
-                for (int c = 0; c < 16; c++) {
-                    cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 1);
-                    cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 2);
-                    if (TPF == 8) cep[c] += __shfl_xor_sync(0xffffffffu, cep[c], 4);
-                }
-#pragma unroll
-                for (int c = 0; c < 16; c++)
-                    if ((c % TPF) == q && live && c < a.dct_len) crow[c] = cep[c];
+                for (int c4 = 0; c4 < 4; c4++)
+                    s_part[(warp * 4 + c4) * kRoundFrames + lane] =
+                        make_float4(cep[4 * c4], cep[4 * c4 + 1], cep[4 * c4 + 2], cep[4 * c4 + 3]);
             }
         }
-        __syncwarp(); // mags are rewritten by the next round's phase 1
+        __syncthreads(); // B: partial cepstra are complete; the magnitudes may be overwritten
+        if (a.dct_len > 0 && lane < nfr) {
+            // warp w sums columns 4w..4w+3 of every frame over the four filter classes, in a fixed order
+            float4 t = s_part[(0 * 4 + warp) * kRoundFrames + lane];
+#pragma unroll
+            for (int w2 = 1; w2 < kFusedWarps; w2++) {
+                const float4 u = s_part[(w2 * 4 + warp) * kRoundFrames + lane];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            float *crow = s_cep + (f0 + lane) * cols + 4 * warp;
+            if (4 * warp + 0 < a.dct_len) crow[0] = t.x;
+            if (4 * warp + 1 < a.dct_len) crow[1] = t.y;
+            if (4 * warp + 2 < a.dct_len) crow[2] = t.z;
+            if (4 * warp + 3 < a.dct_len) crow[3] = t.w;
+        }
     }
     __syncthreads();
 
     // ---- phase 3: every thread owns ONE column (c = tid % cols / col = tid % width) and strides over rows, so the loops
     //      are uniform (no integer division, no stream-dependent branch inside them).
-    float *s_dhat = reinterpret_cast<float *>(smem + L.off_warp);
+    float *s_dhat = reinterpret_cast<float *>(smem + L.off_dhat);
     float *s_dd = reinterpret_cast<float *>(smem + L.off_dd);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;

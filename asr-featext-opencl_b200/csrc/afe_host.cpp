@@ -106,33 +106,6 @@ void build_mel_pairs(const Derived &d, const std::vector<int> &edges, const std:
         }
 }
 
-// Equivalent per-filter form of the same sweep: filter b sums weights[b%2][j] * v[j] over j in [edges[b], edges[b+2])
-// starting from zero (its accumulator is reset when filter b-2 closes at edges[b]). The fused kernel lets the `tpf`
-// lanes of a frame share one filter: lane q takes the 4-bin chunks q, q+tpf, ... of its weight list. Every list
-// therefore starts at a bin that is a multiple of 4 and is zero padded to a multiple of tpf chunks:
-// fidx[b] = {first chunk = first bin / 4, iterations = chunks / tpf (>= 1), offset into wlist in float4 units, 0}.
-void build_filter_lists(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters, int tpf,
-                        std::vector<int> &fidx, std::vector<float> &wlist, int &max_bin)
-{
-    fidx.assign(4 * (size_t)d.nb, 0);
-    wlist.clear();
-    max_bin = 0;
-    for (int b = 0; b < d.nb; b++) {
-        const int j0 = edges[b], j1 = edges[b + 2];
-        int s4 = j0 & ~3;
-        int n4 = j1 > j0 ? (j1 - s4 + 3) / 4 : 1;          // an empty filter still takes one (all-zero) iteration
-        n4 = (n4 + tpf - 1) / tpf * tpf;
-        if (s4 + 4 * n4 > kMagRow) s4 = std::max(0, kMagRow - 4 * n4); // pad at the front instead of past the row end
-        fidx[4 * b + 0] = s4 / 4;
-        fidx[4 * b + 1] = n4 / tpf;
-        fidx[4 * b + 2] = (int)wlist.size() / 4;
-        for (int j = s4; j < s4 + 4 * n4; j++)
-            wlist.push_back(j >= j0 && j < j1 ? filters[(size_t)(b % 2) * d.N2 + j] : 0.f);
-        max_bin = std::max(max_bin, s4 + 4 * n4);
-    }
-    if (wlist.empty()) wlist.assign(4, 0.f);
-}
-
 } // namespace afe
 
 using namespace afe;

@@ -64,10 +64,6 @@ void build_dct(const Derived &d, std::vector<float> &dct);
 void build_mel_pairs(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters,
                      std::vector<float> &pairs /* [bins][2] */);
 
-// per-filter contiguous weight lists: filter b covers bins [edges[b], edges[b+2]) with weights filters[b%2][bin]
-void build_filter_lists(const Derived &d, const std::vector<int> &edges, const std::vector<float> &filters, int tpf,
-                        std::vector<int> &fidx /* int4[nb] */, std::vector<float> &wlist, int &max_bin);
-
 // ---- device-side constant tables for the in-register FFT (afe_fft.cuh)
 struct FftTables {
     float2 *d_tw_a = nullptr;   // [R][16]   exp(-2 pi i n2 k1 / M)
@@ -82,17 +78,12 @@ struct MelTables {              // device copies, rebuilt when alpha changes
     int *d_edges = nullptr;     // [nb+2]
     float *d_pairs = nullptr;   // [bins][2]
     float *d_dct = nullptr;     // [nb][dct_len] (null when ceps_len == 0)
-    int *d_fidx = nullptr;      // int4[nb] per filter: first chunk, iterations, offset into wlist (fused kernel)
-    float *d_wlist = nullptr;   // concatenated per-filter weights, float4 aligned / padded
-    float *d_dct16 = nullptr;   // [nb][16] DCT rows zero padded to 16 columns (fused kernel, LDS.128)
-    int nwl = 0, tpf = 0;       // tpf: phase-2 lanes per frame the lists were built for (0: not built)
     float *d_window = nullptr;  // [W]
     float2 *d_window2 = nullptr; // [M] (w[2n], w[2n+1]) zero padded
     float alpha_built = -1.f;
     void release();
 };
-void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st, int tpf = 0);
-constexpr int kMagRow = 272;    // floats per magnitude row of the fused kernel (bins + zeroed pad for whole-chunk loads)
+void upload_mel_tables(const Derived &d, float alpha, MelTables &t, cudaStream_t st);
 void upload_window(const Derived &d, const float *window, MelTables &t, cudaStream_t st);
 
 // segment + window into float frames [frames][N2] (SegmenterOpenCL::segment_data replacement)

@@ -40,22 +40,18 @@ __global__ void __launch_bounds__(128) k_fft_mag(const int16_t *__restrict__ pcm
 {
     using C = dev::FftCfg<N2>;
     __shared__ float2 scratch[4 * C::FPW * C::SCR];
-    __shared__ float2 s_win[C::M], s_twp[C::M / 2];
     __shared__ float s_dump[C::BINS + 3]; // magnitude row of padding frames
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lf = lane % C::R, fw = lane / C::R;
-    for (int i = threadIdx.x; i < C::M; i += blockDim.x) s_win[i] = window2[i];
-    for (int i = threadIdx.x; i < C::M / 2; i += blockDim.x) s_twp[i] = tw_p[i];
-    float2 twa[16];
-    dev::load_twa<N2>(twa, tw_a, lf);
-    __syncthreads();
+    dev::LaneConsts<N2, NZ> lc;
+    dev::load_lane_consts<N2, NZ>(lc, window2, tw_a, tw_p, lf);
     const int per_iter = 4 * C::FPW;
     for (int f0 = blockIdx.x * per_iter; f0 < frames; f0 += gridDim.x * per_iter) {
         const int f = f0 + warp * C::FPW + fw;
         const bool act = f < frames;
         const int fc = act ? f : frames - 1;
         const uint32_t *words = reinterpret_cast<const uint32_t *>(pcm + (long long)fc * S);
-        dev::fft_frame_mag<N2, NZ, false>(words, s_win, s_twp, twa, scratch + (warp * C::FPW + fw) * C::SCR,
+        dev::fft_frame_mag<N2, NZ, false>(words, lc, scratch + (warp * C::FPW + fw) * C::SCR,
                                           act ? mag + (long long)f * C::BINS : s_dump, lf);
     }
 }
