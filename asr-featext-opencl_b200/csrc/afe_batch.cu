@@ -165,6 +165,7 @@ struct afe_batch {
     double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
+    int warps = 8;            // warps per CTA of the fused kernel (AFE_FUSED_WARPS=4|8)
     FusedSmem L{};
     MelConst mc;
     float mc_alpha = -1.f;
@@ -193,14 +194,14 @@ static void check_fused_support(const Derived &d)
         throw Error("fused batch path supports 256/512-point FFTs (window_size 129..512); use the streaming object");
     if (d.S % 2) throw Error("fused batch path needs an even shift");
     if (d.dct_len > 16) throw Error("fused batch path supports ceps_len + c0 <= 16");
-    if (d.width > kFusedThreads) throw Error("fused batch path supports output width <= 128");
+    if (d.width > 128) throw Error("fused batch path supports output width <= 128");
     if (d.nb > kMaxBanks) throw Error("fused batch path supports num_banks <= 64");
 }
 
 template <int N2> static FusedSmem layout_for(const afe_batch *b)
 {
     const Derived &d = b->d;
-    return fused_smem_layout<N2>(d.S, d.cols, b->tc_max, b->nout_max, d.l2, d.width / d.cols);
+    return fused_smem_layout<N2>(b->warps, d.S, d.cols, b->tc_max, b->nout_max, d.l2, d.width / d.cols);
 }
 
 // Mel weights + DCT matrix as a by-value kernel parameter (constant bank). Per filter b: bins [edges[b], edges[b+2]) with
@@ -227,7 +228,7 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     }
 }
 
-template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+template <int N2, int NZ, int WARPS> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
 {
     const Derived &d = b->d;
     FusedArgs a{};
@@ -249,9 +250,9 @@ template <int N2, int NZ> static void launch_fused(afe_batch *b, const int16_t *
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, NZ, true> : k_fused_mfcc<N2, NZ, false>;
+    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS> : k_fused_mfcc<N2, NZ, false, WARPS>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    kern<<<b->n_tiles, kFusedThreads, b->L.total, b->stream>>>(a, b->L, b->mc);
+    kern<<<b->n_tiles, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
     AFE_CUDA(cudaGetLastError());
     count_launch();
     b->last_launches++;
@@ -266,8 +267,17 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    if (b->d.N2 == 512) pruned ? launch_fused<512, 13>(b, d_pcm, d_out, want_stats) : launch_fused<512, 16>(b, d_pcm, d_out, want_stats);
-    else pruned ? launch_fused<256, 13>(b, d_pcm, d_out, want_stats) : launch_fused<256, 16>(b, d_pcm, d_out, want_stats);
+    const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->warps == 8 ? 1 : 0);
+    switch (key) {
+    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats); break;
+    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats); break;
+    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats); break;
+    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats); break;
+    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats); break;
+    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats); break;
+    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats); break;
+    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats); break;
+    }
 }
 
 static void run_reduce(afe_batch *b)
@@ -361,6 +371,8 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         DeviceGuard g(b->device);
         b->free_plan();
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
+        const char *env_w = getenv("AFE_FUSED_WARPS");
+        if (env_w) b->warps = atoi(env_w) == 4 ? 4 : 8;
         // tile geometry: the cepstra tile holds up to 352 frames (<= 4.6 K floats of shared memory)
         const char *env_tc = getenv("AFE_TILE_FRAMES");
         int tc = env_tc ? atoi(env_tc) : 352;

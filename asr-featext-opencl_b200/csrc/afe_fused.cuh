@@ -65,10 +65,8 @@ struct FusedArgs {
     float rden1, rden2;  // 1 / (2*sum(l^2))
 };
 
-constexpr int kFusedWarps = 4;
-constexpr int kFusedThreads = 32 * kFusedWarps;
-constexpr int kRoundFrames = 32;                      // frames per CTA round
-constexpr int kWarpFrames = kRoundFrames / kFusedWarps; // frames per warp and round
+constexpr int kRoundFrames = 32; // frames per CTA round; WARPS (4 or 8) warps share them, 32/WARPS frames each
+constexpr int kMaxFusedThreads = 256;
 
 struct FusedSmem {
     int off_mbar, off_mags, off_part, off_warp, warp_bytes, w_pcm, w_scratch, pcm_bytes, off_dhat, off_dd, off_red,
@@ -78,28 +76,32 @@ struct FusedSmem {
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 template <int N2>
-FusedSmem fused_smem_layout(int S, int cols, int tc_max, int nout_max, int l2, int nstreams)
+FusedSmem fused_smem_layout(int kFusedWarps, int S, int cols, int tc_max, int nout_max, int l2, int nstreams)
 {
     using C = dev::FftCfg<N2>;
+    const int kWarpFrames = kRoundFrames / kFusedWarps;
     FusedSmem L;
     int o = 0;
     L.off_mbar = o; o += align_up(kFusedWarps * 8, 16);           // one mbarrier per warp, never aliased
     L.off_mags = o; o += align_up(kRoundFrames * C::BINS * 4, 16); // [32][M+1]
-    L.off_part = o; o += kFusedWarps * 4 * kRoundFrames * 16;      // float4 [warp][c4][frame] partial cepstra
-    int w = 0;                                                     // per warp: [pcm | scratch]
+    // per-warp staging [pcm]; then the FFT exchange tiles [scratch], which phase 2 reuses for the partial cepstra
     L.pcm_bytes = align_up(((kWarpFrames - 1) * S + N2) * 2, 16) + 16;
-    L.w_pcm = w; w += L.pcm_bytes;
-    L.w_scratch = w; w += align_up(C::FPW * C::SCR * 8, 16);
-    L.warp_bytes = align_up(w, 128);
+    L.w_pcm = 0;
+    L.warp_bytes = L.pcm_bytes;
     o = align_up(o, 128);
     L.off_warp = o; o += kFusedWarps * L.warp_bytes;
+    o = align_up(o, 128);
+    const int scratch = kFusedWarps * align_up(C::FPW * C::SCR * 8, 16);
+    const int part = kFusedWarps * 4 * kRoundFrames * 16;          // float4 [warp][c4][frame]
+    L.w_scratch = align_up(C::FPW * C::SCR * 8, 16);               // bytes per warp
+    L.off_part = o; o += scratch > part ? scratch : part;
     // phase 3 reuses everything between off_mags and off_cep: [delta rows | delta-delta rows | reduction scratch]
     const int dhat = nstreams >= 2 ? align_up((nout_max + 2 * l2) * cols * 4, 16) : 0;
     const int dd = nstreams >= 3 ? align_up(nout_max * cols * 4, 16) : 0;
     L.off_dhat = L.off_mags;
     L.off_dd = L.off_dhat + dhat;
     L.off_red = L.off_dd + dd;
-    const int phase3_end = L.off_red + kFusedThreads * 4 * 8;
+    const int phase3_end = L.off_red + kMaxFusedThreads * 4 * 8;
     if (phase3_end > o) o = align_up(phase3_end, 128);
     L.off_cep = o; o += align_up(tc_max * cols * 4, 16);
     L.total = o;
@@ -147,12 +149,14 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 } // namespace dev
 
-template <int N2, int NZ, bool FAST>
-__global__ void __launch_bounds__(kFusedThreads, 2)
+template <int N2, int NZ, bool FAST, int kFusedWarps>
+__global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
     using C = dev::FftCfg<N2>;
+    constexpr int kFusedThreads = 32 * kFusedWarps, kWarpFrames = kRoundFrames / kFusedWarps;
     constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, BINS = C::BINS;
+    static_assert(kWarpFrames % FPW == 0, "a warp's frames must fill whole FFT calls");
     extern __shared__ __align__(128) unsigned char smem[];
     float *s_mags = reinterpret_cast<float *>(smem + L.off_mags);
     float4 *s_part = reinterpret_cast<float4 *>(smem + L.off_part);
@@ -164,7 +168,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     unsigned char *wbase = smem + L.off_warp + warp * L.warp_bytes;
     uint64_t *w_mbar = reinterpret_cast<uint64_t *>(smem + L.off_mbar) + warp;
     unsigned char *w_pcm = wbase + L.w_pcm;
-    float2 *w_scratch = reinterpret_cast<float2 *>(wbase + L.w_scratch);
+    float2 *w_scratch = reinterpret_cast<float2 *>(smem + L.off_part + warp * L.w_scratch); // aliased by s_part in phase 2
 
     const Tile tl = a.tiles[blockIdx.x];
     const int D = a.l1 + a.l2, cols = a.cols;
@@ -258,8 +262,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             }
         }
         __syncthreads(); // B: partial cepstra are complete; the magnitudes may be overwritten
-        if (a.dct_len > 0 && lane < nfr) {
-            // warp w sums columns 4w..4w+3 of every frame over the four filter classes, in a fixed order
+        if (a.dct_len > 0 && lane < nfr && warp < 4) {
+            // warp w (< 4) sums columns 4w..4w+3 of every frame over the filter classes, in a fixed order
             float4 t = s_part[(0 * 4 + warp) * kRoundFrames + lane];
 #pragma unroll
             for (int w2 = 1; w2 < kFusedWarps; w2++) {
@@ -272,8 +276,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             if (4 * warp + 2 < a.dct_len) crow[2] = t.z;
             if (4 * warp + 3 < a.dct_len) crow[3] = t.w;
         }
+        __syncthreads(); // C: the partial sums are consumed; their memory is the next round's FFT exchange tile
     }
-    __syncthreads();
 
     // ---- phase 3: every thread owns ONE column (c = tid % cols / col = tid % width) and strides over rows, so the loops
     //      are uniform (no integer division, no stream-dependent branch inside them).
