@@ -103,6 +103,23 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, const int
     if (c == 0) o[2 * width] = counts[g];
 }
 
+// Corpus scope has ONE group over all tiles: two deterministic levels instead of one serial loop.
+// level 1: block j sums tiles j, j+gridDim.x, ... -> scratch[j][width][4]; level 2 = k_reduce_partials over the scratch.
+__global__ void k_reduce_partials_level1(const double *__restrict__ partials, int n_tiles, int width,
+                                         double *__restrict__ scratch)
+{
+    const int c = threadIdx.x;
+    if (c >= width) return;
+    double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const double *p = partials + ((long long)t * width + c) * 4;
+        s0 += p[0]; s1 += p[1];
+        lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+    }
+    double *o = scratch + ((long long)blockIdx.x * width + c) * 4;
+    o[0] = s0; o[1] = s1; o[2] = lo; o[3] = hi;
+}
+
 // mean / scale per group and column (normalizercpu.cpp:31-66). With norm_after_dyn == 0 the reference normalises the
 // statics before the deltas are taken, which equals scaling delta columns by the static column's scale (mean 0).
 __global__ void k_finalize_stats(const double *__restrict__ stats, int width, int cols, int norm_type, int norm_after_dyn,
@@ -137,6 +154,7 @@ __global__ void k_normalize_tiles(float *__restrict__ out, const Tile *__restric
     }
 }
 
+constexpr int kCorpusBlocks = 296; // 2 per SM
 static std::atomic<int> g_launches{0};
 int kernel_launch_count() { return g_launches.load(); }
 void count_launch(int n) { g_launches.fetch_add(n); }
@@ -162,7 +180,8 @@ struct afe_batch {
     int64_t pcm_extent = 0;
     Tile *d_tiles = nullptr;
     int *d_tile_begin = nullptr;
-    double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr;
+    double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr, *d_scratch = nullptr;
+    int *d_scratch_begin = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
     int warps = 8;            // warps per CTA of the fused kernel (AFE_FUSED_WARPS=4|8)
@@ -182,6 +201,9 @@ struct afe_batch {
         if (d_counts) cudaFree(d_counts);
         if (d_partials) cudaFree(d_partials);
         if (d_stats) cudaFree(d_stats);
+        if (d_scratch) cudaFree(d_scratch);
+        if (d_scratch_begin) cudaFree(d_scratch_begin);
+        d_scratch = nullptr; d_scratch_begin = nullptr;
         if (d_mean) cudaFree(d_mean);
         if (d_scale) cudaFree(d_scale);
         d_tiles = nullptr; d_tile_begin = nullptr; d_counts = d_partials = d_stats = nullptr; d_mean = d_scale = nullptr;
@@ -214,17 +236,19 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
         if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     memset(&mc, 0, sizeof mc);
-    int off = 0;
+    int off4 = 0;
     for (int b = 0; b < d.nb; b++) {
-        const int j0 = edges[b], n = edges[b + 2] - edges[b];
-        if (off + n > kMaxWl) throw Error("mel weight list exceeds the kernel-parameter budget");
-        mc.fstart[b] = (short)j0; mc.flen[b] = (short)n; mc.woff[b] = (short)off;
-        for (int j = 0; j < n; j++) mc.wl[off + j] = filters[(size_t)(b % 2) * d.N2 + j0 + j];
-        off += n;
+        const int j0 = edges[b], n = edges[b + 2] - edges[b], n4 = (n + 3) / 4;
+        if (off4 + n4 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
+        mc.fstart[b] = (short)j0; mc.n4[b] = (short)n4; mc.woff4[b] = (short)off4;
+        float *w = reinterpret_cast<float *>(mc.wl4 + off4);
+        for (int j = 0; j < n; j++) w[j] = filters[(size_t)(b % 2) * d.N2 + j0 + j];
+        off4 += n4;
     }
     if (d.C > 0) {
         build_dct(d, dct);
-        memcpy(mc.dct, dct.data(), sizeof(float) * dct.size());
+        for (int k = 0; k < d.nb; k++)
+            for (int j = 0; j < d.dct_len; j++) reinterpret_cast<float *>(mc.dct4[k])[j] = dct[(size_t)k * d.dct_len + j];
     }
 }
 
@@ -282,6 +306,14 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
 
 static void run_reduce(afe_batch *b)
 {
+    if (b->scope == AFE_STATS_CORPUS && b->n_tiles > 2 * kCorpusBlocks) {
+        k_reduce_partials_level1<<<kCorpusBlocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, b->d.width, b->d_scratch);
+        AFE_CUDA(cudaGetLastError());
+        k_reduce_partials<<<1, 128, 0, b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, b->d.width, b->d_stats);
+        AFE_CUDA(cudaGetLastError());
+        count_launch(2); b->last_launches += 2;
+        return;
+    }
     k_reduce_partials<<<b->n_groups, 128, 0, b->stream>>>(b->d_partials, b->d_tile_begin, b->d_counts, b->d.width, b->d_stats);
     AFE_CUDA(cudaGetLastError());
     count_launch(); b->last_launches++;
@@ -437,6 +469,12 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             AFE_CUDA(cudaMemcpy(b->d_counts, counts.data(), sizeof(double) * counts.size(), cudaMemcpyHostToDevice));
             AFE_CUDA(cudaMalloc(&b->d_partials, sizeof(double) * 4 * w * tiles.size()));
             AFE_CUDA(cudaMalloc(&b->d_stats, sizeof(double) * (4 * w + 1) * b->n_groups));
+            if (corpus) {
+                const int sb[2] = {0, kCorpusBlocks};
+                AFE_CUDA(cudaMalloc(&b->d_scratch, sizeof(double) * 4 * w * kCorpusBlocks));
+                AFE_CUDA(cudaMalloc(&b->d_scratch_begin, sizeof(sb)));
+                AFE_CUDA(cudaMemcpy(b->d_scratch_begin, sb, sizeof(sb), cudaMemcpyHostToDevice));
+            }
             AFE_CUDA(cudaMalloc(&b->d_mean, sizeof(float) * w * b->n_groups));
             AFE_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * w * b->n_groups));
         }

@@ -38,16 +38,16 @@ struct Tile {
 };
 
 constexpr int kMaxBanks = 64;
-constexpr int kMaxWl = 2 * 257 + 2;   // weights: every bin feeds one rising and one falling side
-constexpr int kMaxDct = kMaxBanks * 16;
+constexpr int kMaxWl4 = (2 * 257 + 3 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists padded to 4
 
-// Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only.
+// Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only,
+// read with 128-bit constant loads. Weight lists are zero padded to a multiple of 4 bins; DCT rows to 16 columns.
 struct MelConst {
-    float wl[kMaxWl];            // concatenated per-filter weights: filter b = wl[woff[b] .. woff[b]+flen[b])
-    float dct[kMaxDct];          // [nb][dct_len]
+    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + n4[b]), bins fstart[b] + 4*i + {0,1,2,3}
+    float4 dct4[kMaxBanks][4];   // [nb][16]
     short fstart[kMaxBanks];     // first bin of filter b  (= edges[b])
-    short flen[kMaxBanks];       // bins of filter b       (= edges[b+2]-edges[b])
-    short woff[kMaxBanks];
+    short n4[kMaxBanks];         // 4-bin chunks of filter b (= ceil((edges[b+2]-edges[b]) / 4))
+    short woff4[kMaxBanks];
 };
 
 struct FusedArgs {
@@ -83,7 +83,7 @@ FusedSmem fused_smem_layout(int kFusedWarps, int S, int cols, int tc_max, int no
     FusedSmem L;
     int o = 0;
     L.off_mbar = o; o += align_up(kFusedWarps * 8, 16);           // one mbarrier per warp, never aliased
-    L.off_mags = o; o += align_up(kRoundFrames * C::BINS * 4, 16); // [32][M+1]
+    L.off_mags = o; o += align_up((kRoundFrames * C::BINS + 4) * 4, 16); // [32][M+1] + pad for whole-chunk reads
     // per-warp staging [pcm]; then the FFT exchange tiles [scratch], which phase 2 reuses for the partial cepstra
     L.pcm_bytes = align_up(((kWarpFrames - 1) * S + N2) * 2, 16) + 16;
     L.w_pcm = 0;
@@ -193,6 +193,9 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     }
     dev::LaneConsts<N2, NZ> lc;
     dev::load_lane_consts<N2, NZ>(lc, a.window2, a.tw_a, a.tw_p, lf);
+    // phase 2 reads whole 4-bin chunks: up to 3 floats past a filter's end, i.e. into the next row (or the pad) with a
+    // ZERO weight. Rows of frames that are never computed (short tiles) must therefore hold finite numbers.
+    for (int i = tid; i < kRoundFrames * BINS + 4; i += kFusedThreads) s_mags[i] = 0.f;
     __syncthreads();
 
     uint32_t parity = 0;
@@ -239,18 +242,28 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
 #pragma unroll
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
             for (int b = warp; b < a.nb; b += kFusedWarps) {
-                const int j0 = mc.fstart[b], n = mc.flen[b];
-                const float *wv = mc.wl + mc.woff[b];
-                const float *mv = mrow + j0;
+                const int n4 = mc.n4[b];
+                const float4 *wv = mc.wl4 + mc.woff4[b];
+                const float *mv = mrow + mc.fstart[b];
                 float acc = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < n; i++) acc = fmaf(wv[i], mv[i], acc); // ascending bins, like the reference sweep
+#pragma unroll 2
+                for (int i = 0; i < n4; i++) { // ascending bins, like the reference sweep
+                    const float4 w = wv[i];
+                    acc = fmaf(w.x, mv[4 * i + 0], acc);
+                    acc = fmaf(w.y, mv[4 * i + 1], acc);
+                    acc = fmaf(w.z, mv[4 * i + 2], acc);
+                    acc = fmaf(w.w, mv[4 * i + 3], acc);
+                }
                 const float e = dev::mel_log<FAST>(acc);
                 if (a.dct_len > 0) {
-                    const float *drow = mc.dct + b * a.dct_len;
 #pragma unroll
-                    for (int c = 0; c < 16; c++)
-                        if (c < a.dct_len) cep[c] = fmaf(e, drow[c], cep[c]);
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 d4 = mc.dct4[b][c4];
+                        cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
+                        cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
+                        cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
+                        cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
+                    }
                 } else
                     s_cep[(f0 + lane) * cols + b] = e;
             }

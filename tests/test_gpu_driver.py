@@ -1,0 +1,71 @@
+"""GPU tier: the C++ host mirror (host/afe_stage_api.hpp + host/mfcccuda.hpp) driven by the reference's block loop in
+host/afe_extract.cpp — text layout `| %f | %f | ... |` (ASR_OCL.cpp:252-260) incl. the ms/Hz timestamps (Q6)."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from common import assert_close
+from golden_io import load_pcm
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ol.ROOT, "asr-featext-opencl_b200", "afe_extract")
+
+
+def write_wav(path, pcm, sr=16000):
+    data = np.ascontiguousarray(pcm, "<i2").tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, sr, sr * 2, 2, 16)
+    hdr += b"data" + struct.pack("<I", len(data))
+    assert len(hdr) == 44
+    open(path, "wb").write(hdr + data)
+
+
+def run(args):
+    if not os.path.exists(EXE):
+        pytest.skip("afe_extract not built")
+    r = subprocess.run([EXE] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+@pytest.mark.parametrize("limit", [10_000_000, 16000])
+def test_text_output_matches_reference_layout_and_values(oracle, tmp_path, limit):
+    pcm = load_pcm()["a1"]
+    wav, out = str(tmp_path / "a1.wav"), str(tmp_path / "a1.txt")
+    write_wav(wav, pcm)
+    run(["--banks", "23", "--ceps", "12", "--c0", "1", "--norm", "1", "--dyn", "2", "--l1", "3", "--l2", "3",
+         "--sample-limit", str(limit), wav, out])
+    lines = open(out).read().splitlines()
+    assert len(lines) == 504
+    pat = re.compile(r"^\| -?\d+\.\d{6} \|( -?\d+\.\d{6} \|){39}$")
+    assert all(pat.match(l) for l in lines), lines[0]
+    vals = np.array([[float(x) for x in l.strip("| ").split(" | ")] for l in lines])
+    # Q6: time = 0.5f*window_ms/sr + t*(shift_ms/sr) = 0.00078125 + t*0.000625 (ms divided by Hz)
+    np.testing.assert_allclose(vals[:, 0], 0.5 * 25 / 16000 + np.arange(504) * (10 / 16000), atol=1e-6)
+    p = ol.default_params(norm="cmn", dyn="acc")
+    want = oracle.extract(p, [pcm], sample_limit=limit if limit < len(pcm) else 1 << 22)[0][0]
+    got = vals[:, 1:].astype(np.float32)
+    assert np.abs(got - want).max() < 5e-4 + 1e-6   # %f keeps 6 decimals
+    assert_close(got, np.round(want.astype(np.float64), 6).astype(np.float32), p, "text")
+
+
+def test_binary_output_and_nist_header(oracle, tmp_path):
+    pcm = load_pcm()["sample1"]
+    nist = str(tmp_path / "s.wav")
+    open(nist, "wb").write(b"NIST_1A\n   1024\n".ljust(1024, b" ") + np.ascontiguousarray(pcm, "<i2").tobytes())  # SPHERE: 1024-byte header
+    out = str(tmp_path / "s.bin")
+    run(["--banks", "23", "--norm", "0", "--dyn", "0", "--text-output", "0", nist, out])
+    got = np.fromfile(out, np.float32).reshape(-1, 13)
+    want = oracle.extract(ol.default_params(), [pcm], sample_limit=1 << 22)[0][0]
+    assert_close(got, want, ol.default_params(), "binary")
+
+
+def test_driver_reports_reference_error_strings(tmp_path):
+    wav = str(tmp_path / "short.wav")
+    write_wav(wav, np.zeros(400 + 160 * 5, np.int16))
+    r = subprocess.run([EXE, "--dyn", "2", wav, str(tmp_path / "o.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "window count is too small" in r.stderr

@@ -304,6 +304,31 @@ def test_batch_equals_stream_object():
 
 
 # ---------------------------------------------------------------------------------------------- corpus CMVN
+def test_corpus_cmvn_many_tiles_two_level_reduction():
+    """> 592 tiles: the corpus statistics take the two-level reduction; must equal NumPy on the raw features."""
+    p = ol.default_params(norm="cvn", dyn="acc")
+    utts = synth_utterances(700, 6000, seed=33, ragged=True)
+    utts = [u for u in utts if len(u) >= 240 + 160 * 14]
+    ap = to_afe_params(p, BIG)
+    b = afe.BatchMfcc(ap, 0, stats_scope=afe.STATS_CORPUS)
+    pcm, offs, lens = afe.pack_utterances(utts)
+    total = b.plan(offs, lens)
+    assert b.num_tiles > 592
+    d_pcm = afe.DeviceBuffer(pcm.nbytes + 64); d_pcm.upload(pcm)
+    d_out = afe.DeviceBuffer(total * 39 * 4)
+    b.extract_device(d_pcm.ptr.value, d_out.ptr.value)
+    b.synchronize()
+    raw = d_out.download((total, 39), np.float32).astype(np.float64)
+    b.corpus_stats()
+    b.normalize_device(d_out.ptr.value)
+    b.synchronize()
+    got = d_out.download((total, 39), np.float32)
+    n = len(raw)
+    want = (raw - raw.mean(0)) * np.sqrt((n - 1) / ((raw * raw).sum(0) - raw.sum(0) ** 2 / n))
+    np.testing.assert_allclose(got, want, atol=2e-5)
+    b.close(); d_pcm.free(); d_out.free()
+
+
 @pytest.mark.parametrize("norm", ["cmn", "cvn", "minmax"])
 def test_corpus_cmvn_two_shards_equal_one(norm):
     """Corpus statistics: (a) one batch; (b) two 'ranks' over disjoint utterance shards whose statistics records are
