@@ -58,7 +58,9 @@ static void process_file(ParamBase *param, const Config &cfg, const std::string 
     FILE *fout = fopen(out.c_str(), cfg.text_output ? "w" : "wb");
     if (!fout) throw std::runtime_error("Can't create output file: " + out);
     const int limit = param->get_input_buffer_size(), width = param->get_output_data_width();
-    std::vector<float> rows((size_t)width * std::max(1, param->estimated_window_count(limit)));
+    // a middle block can return more rows than estimated_window_count(limit) (carry-over): size for the object's frame
+    // capacity, input_window_limit + 2 + 3*(l1+l2) (mfcccpu.cpp:95-103)
+    std::vector<float> rows((size_t)width * (size_t)(std::max(1, param->estimated_window_count(limit)) + 2 + 3 * (cfg.delta_l1 + cfg.delta_l2)));
     long total = 0;
     size_t pos = 0;
     while (pos < pcm.size()) { // ASR_OCL.cpp:227-267
