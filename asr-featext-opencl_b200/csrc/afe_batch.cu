@@ -176,7 +176,10 @@ struct afe_batch {
     // plan
     int n_utts = 0, n_tiles = 0, n_groups = 0;
     bool aligned = false;
-    std::vector<int64_t> sample_off, frame_off;
+    std::vector<int64_t> sample_off, sample_len, frame_off;
+    std::vector<int> h_tile_begin;          // [n_utts+1] first tile of every utterance
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
     int64_t pcm_extent = 0;
     Tile *d_tiles = nullptr;
     int *d_tile_begin = nullptr;
@@ -252,13 +255,14 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     }
 }
 
-template <int N2, int NZ, int WARPS> static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats)
+template <int N2, int NZ, int WARPS>
+static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1)
 {
     const Derived &d = b->d;
     FusedArgs a{};
-    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles;
+    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles + t0;
     a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.partials = want_stats ? b->d_partials : nullptr;
+    a.partials = want_stats ? b->d_partials + (size_t)t0 * d.width * 4 : nullptr;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
     a.q1 = (b->flags & AFE_BATCH_Q1_EXACT) && d.D > 0 ? 1 : 0;
@@ -276,56 +280,66 @@ template <int N2, int NZ, int WARPS> static void launch_fused(afe_batch *b, cons
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
     auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS> : k_fused_mfcc<N2, NZ, false, WARPS>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    kern<<<b->n_tiles, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
+    kern<<<t1 - t0, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
     AFE_CUDA(cudaGetLastError());
     count_launch();
     b->last_launches++;
 }
 
-static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out)
+static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1)
 {
+    if (t1 < 0) t1 = b->n_tiles;
+    if (t1 <= t0) return;
     if (!b->window_set) throw Error("set_window must be called before running");
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
     if (b->mc_alpha != b->alpha) { build_mel_const(b->d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
-    b->last_launches = 0;
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
     const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->warps == 8 ? 1 : 0);
     switch (key) {
-    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats); break;
-    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats); break;
-    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats); break;
-    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats); break;
-    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats); break;
-    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats); break;
-    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats); break;
-    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats); break;
+    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
     }
 }
 
-static void run_reduce(afe_batch *b)
+static void run_reduce(afe_batch *b, int g0 = 0, int g1 = -1)
 {
+    if (g1 < 0) g1 = b->n_groups;
+    if (g1 <= g0) return;
+    const int w = b->d.width;
     if (b->scope == AFE_STATS_CORPUS && b->n_tiles > 2 * kCorpusBlocks) {
-        k_reduce_partials_level1<<<kCorpusBlocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, b->d.width, b->d_scratch);
+        k_reduce_partials_level1<<<kCorpusBlocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, w, b->d_scratch);
         AFE_CUDA(cudaGetLastError());
-        k_reduce_partials<<<1, 128, 0, b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, b->d.width, b->d_stats);
+        k_reduce_partials<<<1, 128, 0, b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, w, b->d_stats);
         AFE_CUDA(cudaGetLastError());
         count_launch(2); b->last_launches += 2;
         return;
     }
-    k_reduce_partials<<<b->n_groups, 128, 0, b->stream>>>(b->d_partials, b->d_tile_begin, b->d_counts, b->d.width, b->d_stats);
+    k_reduce_partials<<<g1 - g0, 128, 0, b->stream>>>(b->d_partials, b->d_tile_begin + g0, b->d_counts + g0, w,
+                                                       b->d_stats + (size_t)g0 * (4 * w + 1));
     AFE_CUDA(cudaGetLastError());
     count_launch(); b->last_launches++;
 }
 
-static void run_normalize(afe_batch *b, float *d_out)
+static void run_normalize(afe_batch *b, float *d_out, int t0 = 0, int t1 = -1, int g0 = 0, int g1 = -1)
 {
     const Derived &d = b->d;
-    k_finalize_stats<<<b->n_groups, 128, 0, b->stream>>>(b->d_stats, d.width, d.cols, d.p.norm, d.p.norm_after_dyn,
-                                                        b->d_mean, b->d_scale);
+    if (t1 < 0) t1 = b->n_tiles;
+    if (g1 < 0) g1 = b->n_groups;
+    if (t1 <= t0 || g1 <= g0) return;
+    const size_t w = d.width;
+    k_finalize_stats<<<g1 - g0, 128, 0, b->stream>>>(b->d_stats + (size_t)g0 * (4 * w + 1), d.width, d.cols, d.p.norm,
+                                                      d.p.norm_after_dyn, b->d_mean + g0 * w, b->d_scale + g0 * w);
     AFE_CUDA(cudaGetLastError());
-    k_normalize_tiles<<<b->n_tiles, 256, 0, b->stream>>>(d_out, b->d_tiles, d.width, d.p.norm, b->d_mean, b->d_scale);
+    // Tile::group is absolute, so mean / scale keep their base
+    k_normalize_tiles<<<t1 - t0, 256, 0, b->stream>>>(d_out, b->d_tiles + t0, d.width, d.p.norm, b->d_mean, b->d_scale);
     AFE_CUDA(cudaGetLastError());
     count_launch(2); b->last_launches += 2;
 }
@@ -365,6 +379,10 @@ void afe_batch_destroy(afe_batch *b)
     if (b->d_pcm_stage) cudaFree(b->d_pcm_stage);
     if (b->d_out_stage) cudaFree(b->d_out_stage);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    if (b->s_in) cudaStreamDestroy(b->s_in);
+    if (b->s_out) cudaStreamDestroy(b->s_out);
+    for (auto e : b->ev_in) cudaEventDestroy(e);
+    for (auto e : b->ev_k) cudaEventDestroy(e);
     delete b;
 }
 
@@ -413,6 +431,8 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->tc_max = tc; b->nout_max = tc - 2 * d.D;
         b->n_utts = n_utts;
         b->sample_off.assign(off, off + n_utts);
+        b->sample_len.assign(len, len + n_utts);
+        b->h_tile_begin.assign(n_utts + 1, 0);
         b->pcm_extent = 0;
         b->frame_off.assign(n_utts + 1, 0);
         std::vector<Tile> tiles;
@@ -442,6 +462,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
                 if (cost < best_cost) { best_cost = cost; ntile = cand; }
             }
             const int nout = (T + ntile - 1) / ntile;
+            b->h_tile_begin[u] = (int)tiles.size();
             if (!corpus) tile_begin.push_back((int)tiles.size());
             for (int t0 = 0; t0 < T; t0 += nout) {
                 Tile tl;
@@ -454,6 +475,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         }
         if (corpus) { tile_begin.push_back(0); counts.push_back(corpus_count); }
         tile_begin.push_back((int)tiles.size());
+        b->h_tile_begin[n_utts] = (int)tiles.size();
         b->aligned = aligned;
         b->n_tiles = (int)tiles.size();
         b->n_groups = corpus ? 1 : n_utts;
@@ -492,7 +514,7 @@ int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
 
 int afe_batch_extract_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
 {
-    return guarded([&] { DeviceGuard g(b->device); run_extract(b, d_pcm, d_out); });
+    return guarded([&] { DeviceGuard g(b->device); b->last_launches = 0; run_extract(b, d_pcm, d_out); });
 }
 
 int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
@@ -501,6 +523,7 @@ int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
         DeviceGuard g(b->device);
         if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
             throw Error("corpus statistics need the two-pass sequence: extract_device, corpus_stats, allreduce, normalize_device");
+        b->last_launches = 0;
         run_extract(b, d_pcm, d_out);
         if (b->d.p.norm != AFE_NORM_NONE) { run_reduce(b); run_normalize(b, d_out); }
     });
@@ -552,14 +575,19 @@ int afe_batch_synchronize(afe_batch *b)
     return guarded([&] { DeviceGuard g(b->device); AFE_CUDA(cudaStreamSynchronize(b->stream)); });
 }
 
-// End-to-end with host buffers. h_pcm should be pinned for full PCIe speed (works with pageable memory too).
+// End-to-end with host buffers. h_pcm / h_out should be pinned for full PCIe speed (pageable memory works too).
+// The shard is cut into up to 32 utterance chunks and pipelined over three streams: H2D of chunk c+1, the kernels of
+// chunk c and D2H of chunk c-1 overlap (PCIe is full duplex), so the call is bound by max(H2D, D2H) instead of their sum.
 int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
 {
     return guarded([&] {
         DeviceGuard g(b->device);
+        const Derived &d = b->d;
         if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
+        if (b->scope == AFE_STATS_CORPUS && d.p.norm != AFE_NORM_NONE)
+            throw Error("run_host: corpus statistics need the two-pass device sequence");
         const size_t n_samples = (size_t)b->pcm_extent;
-        const size_t pcm_bytes = n_samples * 2 + 32, out_bytes = (size_t)b->frame_off.back() * b->d.width * 4;
+        const size_t pcm_bytes = n_samples * 2 + 32, out_bytes = (size_t)b->frame_off.back() * d.width * 4;
         if (pcm_bytes > b->pcm_stage_bytes) {
             if (b->d_pcm_stage) cudaFree(b->d_pcm_stage);
             AFE_CUDA(cudaMalloc(&b->d_pcm_stage, pcm_bytes));
@@ -570,12 +598,40 @@ int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
             AFE_CUDA(cudaMalloc(&b->d_out_stage, out_bytes));
             b->out_stage_bytes = out_bytes;
         }
-        AFE_CUDA(cudaMemcpyAsync(b->d_pcm_stage, h_pcm, n_samples * 2, cudaMemcpyHostToDevice, b->stream));
-        if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
-            throw Error("run_host: corpus statistics need the two-pass device sequence");
-        run_extract(b, b->d_pcm_stage, b->d_out_stage);
-        if (b->d.p.norm != AFE_NORM_NONE) { run_reduce(b); run_normalize(b, b->d_out_stage); }
-        AFE_CUDA(cudaMemcpyAsync(h_out, b->d_out_stage, out_bytes, cudaMemcpyDeviceToHost, b->stream));
+        if (!b->s_in) {
+            AFE_CUDA(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+            AFE_CUDA(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+        }
+        // chunks are contiguous in samples only when the utterances are packed in increasing order
+        bool ordered = true;
+        for (int u = 0; u + 1 < b->n_utts; u++) ordered = ordered && b->sample_off[u] + b->sample_len[u] <= b->sample_off[u + 1];
+        const int n_chunks = ordered ? std::max(1, std::min(32, b->n_utts / 8)) : 1;
+        while ((int)b->ev_in.size() < n_chunks) {
+            cudaEvent_t e1, e2;
+            AFE_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            AFE_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            b->ev_in.push_back(e1); b->ev_k.push_back(e2);
+        }
+        b->last_launches = 0;
+        if (b->mc_alpha != b->alpha) { build_mel_const(d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
+        const bool norm = d.p.norm != AFE_NORM_NONE;
+        for (int c = 0; c < n_chunks; c++) {
+            const int u0 = (int)((int64_t)b->n_utts * c / n_chunks), u1 = (int)((int64_t)b->n_utts * (c + 1) / n_chunks);
+            if (u1 <= u0) continue;
+            const int64_t s0 = n_chunks == 1 ? 0 : b->sample_off[u0];
+            const int64_t s1 = n_chunks == 1 ? (int64_t)n_samples : b->sample_off[u1 - 1] + b->sample_len[u1 - 1];
+            AFE_CUDA(cudaMemcpyAsync(b->d_pcm_stage + s0, h_pcm + s0, (size_t)(s1 - s0) * 2, cudaMemcpyHostToDevice, b->s_in));
+            AFE_CUDA(cudaEventRecord(b->ev_in[c], b->s_in));
+            AFE_CUDA(cudaStreamWaitEvent(b->stream, b->ev_in[c], 0));
+            const int t0 = b->h_tile_begin[u0], t1 = b->h_tile_begin[u1];
+            run_extract(b, b->d_pcm_stage, b->d_out_stage, t0, t1);
+            if (norm) { run_reduce(b, u0, u1); run_normalize(b, b->d_out_stage, t0, t1, u0, u1); }
+            AFE_CUDA(cudaEventRecord(b->ev_k[c], b->stream));
+            AFE_CUDA(cudaStreamWaitEvent(b->s_out, b->ev_k[c], 0));
+            const size_t r0 = (size_t)b->frame_off[u0] * d.width, r1 = (size_t)b->frame_off[u1] * d.width;
+            AFE_CUDA(cudaMemcpyAsync(h_out + r0, b->d_out_stage + r0, (r1 - r0) * 4, cudaMemcpyDeviceToHost, b->s_out));
+        }
+        AFE_CUDA(cudaStreamSynchronize(b->s_out));
         AFE_CUDA(cudaStreamSynchronize(b->stream));
     });
 }

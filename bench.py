@@ -113,6 +113,7 @@ def run_reference(args):
 
 
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background; stop(t0, t1) keeps the samples taken inside the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -121,7 +122,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -129,22 +130,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        rows = inside if len(inside) >= 2 else [r for (_, r) in self.rows]
+        sm, mx, power, reasons = [], 0, [], set()
+        for r in rows:
             try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                sm.append(float(r[1])); mx = max(mx, float(r[2])); power.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": len(inside), "power_w_max": max(power) if power else None}
 
 
 def run_b200(args):
@@ -201,12 +204,13 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     ev_mid = torch.cuda.Event(enable_timing=True)
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    t_begin = time.perf_counter()
     k1_ms, launches = [], 0
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -217,9 +221,10 @@ def run_b200(args):
         launches += b.kernel_launches                         # K1 + K2 reduce + K2 finalize + K3 = 4 per step
         ev0[i + 1].record(stream)
     barrier()
+    t_end = time.perf_counter()
     total_ms = ev0[0].elapsed_time(ev0[-1])
     k1_ms = [ev0[i].elapsed_time(mids[i]) for i in range(args.steps)]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -314,7 +319,9 @@ def run_b200(args):
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                roof["traffic"] = json.load(open(prof)).get("k_fused_mfcc_dram_bytes_per_launch")
+                per_frame = json.load(open(prof)).get("k_fused_mfcc_dram_bytes_per_frame")
+                roof["traffic"] = per_frame * frames if per_frame else None   # ncu dram read+write per frame x frames/launch
+                roof["traffic_source"] = "profiles/traffic.json (ncu --set full on a 2000-utterance launch, scaled per frame)"
             except Exception:
                 pass
         cpu = None
@@ -347,7 +354,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU (BASELINE config 3: 10000)")
