@@ -240,13 +240,14 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     memset(&mc, 0, sizeof mc);
     int off4 = 0;
+    const float scale = 0.5f / (float)d.N2; // the kernel stores |2X|; scaling by a power of two commutes with rounding
     for (int b = 0; b < d.nb; b++) {
-        const int j0 = edges[b], n = edges[b + 2] - edges[b], n4 = (n + 3) / 4;
-        if (off4 + n4 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
-        mc.fstart[b] = (short)j0; mc.n4[b] = (short)n4; mc.woff4[b] = (short)off4;
+        const int j0 = edges[b], n = edges[b + 2] - edges[b], n8 = (n + 7) / 8;
+        if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
+        mc.fstart[b] = (short)j0; mc.n8[b] = (short)n8; mc.woff4[b] = (short)off4;
         float *w = reinterpret_cast<float *>(mc.wl4 + off4);
-        for (int j = 0; j < n; j++) w[j] = filters[(size_t)(b % 2) * d.N2 + j0 + j];
-        off4 += n4;
+        for (int j = 0; j < n; j++) w[j] = filters[(size_t)(b % 2) * d.N2 + j0 + j] * scale;
+        off4 += 2 * n8;
     }
     if (d.C > 0) {
         build_dct(d, dct);

@@ -157,7 +157,9 @@ template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
 //   lc       : this lane's window pairs and twiddles (registers)
 //   scratch  : this frame's exchange tile, FftCfg::SCR float2
 //   mag_out  : BINS floats (always written; padding frames point at a row nobody reads)
-template <int N2, int NZ, bool FAST>
+//   SCALED   : true -> |X|/N2 (reference value); false -> |2X| (= 2*N2 times that; the caller folds the exact
+//              power-of-two factor 0.5/N2 into its mel weights)
+template <int N2, int NZ, bool FAST, bool SCALED = true>
 __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneConsts<N2, NZ> &lc, float2 *scratch,
                                               float *mag_out, int lf)
 {
@@ -224,12 +226,14 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneC
         const float pr = dr * w.x - di * w.y, pi = dr * w.y + di * w.x;
         const float x1r = sr + pi, x1i = si - pr;   // 2 X[k]
         const float x2r = sr - pi, x2i = si + pr;   // 2 conj(X[M-k])
-        mf[R * m] = mag_sqrt<FAST>(x1r * x1r + x1i * x1i) * scale;
-        mr[-R * m] = mag_sqrt<FAST>(x2r * x2r + x2i * x2i) * scale;
+        const float v1 = mag_sqrt<FAST>(x1r * x1r + x1i * x1i), v2 = mag_sqrt<FAST>(x2r * x2r + x2i * x2i);
+        mf[R * m] = SCALED ? v1 * scale : v1;
+        mr[-R * m] = SCALED ? v2 * scale : v2;
     }
     if (lf == 0) {
         const float2 a = scratch[M / 2]; // X[M/2] = conj(Z[M/2])
-        mag_out[M / 2] = mag_sqrt<FAST>(a.x * a.x + a.y * a.y) * (1.0f / (float)N2);
+        const float vm = mag_sqrt<FAST>(a.x * a.x + a.y * a.y);
+        mag_out[M / 2] = SCALED ? vm * (1.0f / (float)N2) : vm + vm;
     }
     __syncwarp();
 }

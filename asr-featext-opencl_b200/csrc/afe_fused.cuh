@@ -38,15 +38,16 @@ struct Tile {
 };
 
 constexpr int kMaxBanks = 64;
-constexpr int kMaxWl4 = (2 * 257 + 3 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists padded to 4
+constexpr int kMaxWl4 = (2 * 257 + 7 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists padded to 8
 
 // Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only,
 // read with 128-bit constant loads. Weight lists are zero padded to a multiple of 4 bins; DCT rows to 16 columns.
 struct MelConst {
-    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + n4[b]), bins fstart[b] + 4*i + {0,1,2,3}
+    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + 2*n8[b]), bins fstart[b] + 8*i + {0..7}; the weights
+                                 // carry the 0.5/N2 magnitude scale (an exact power of two), see fft_frame_mag
     float4 dct4[kMaxBanks][4];   // [nb][16]
     short fstart[kMaxBanks];     // first bin of filter b  (= edges[b])
-    short n4[kMaxBanks];         // 4-bin chunks of filter b (= ceil((edges[b+2]-edges[b]) / 4))
+    short n8[kMaxBanks];         // 8-bin chunks of filter b (= ceil((edges[b+2]-edges[b]) / 8))
     short woff4[kMaxBanks];
 };
 
@@ -83,7 +84,7 @@ FusedSmem fused_smem_layout(int kFusedWarps, int S, int cols, int tc_max, int no
     FusedSmem L;
     int o = 0;
     L.off_mbar = o; o += align_up(kFusedWarps * 8, 16);           // one mbarrier per warp, never aliased
-    L.off_mags = o; o += align_up((kRoundFrames * C::BINS + 4) * 4, 16); // [32][M+1] + pad for whole-chunk reads
+    L.off_mags = o; o += align_up((kRoundFrames * C::BINS + 8) * 4, 16); // [32][M+1] + pad for whole-chunk reads
     // per-warp staging [pcm]; then the FFT exchange tiles [scratch], which phase 2 reuses for the partial cepstra
     L.pcm_bytes = align_up(((kWarpFrames - 1) * S + N2) * 2, 16) + 16;
     L.w_pcm = 0;
@@ -149,6 +150,45 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 } // namespace dev
 
+namespace dev {
+
+// regression numerator sum_l l*(p[+l*stride] - p[-l*stride]); L == 3 (the reference's default l1 = l2 = 3) is unrolled
+__device__ __forceinline__ float delta_num(const float *p, int stride, int L)
+{
+    if (L == 3) {
+        float num = p[stride] - p[-stride];
+        num = fmaf(2.f, p[2 * stride] - p[-2 * stride], num);
+        return fmaf(3.f, p[3 * stride] - p[-3 * stride], num);
+    }
+    float num = 0.f;
+    for (int l = 1; l <= L; l++) num = fmaf((float)l, p[l * stride] - p[-l * stride], num);
+    return num;
+}
+
+// rows out + column statistics of one thread's column. KIND: 0 none, 1 sums, 2 + sums of squares, 3 + min/max
+template <int KIND>
+__device__ __forceinline__ void write_rows(float *__restrict__ orow, const float *__restrict__ src, int r_off, int rpp, int nout,
+                                           int rq, int rs, int cols, int width, int D, double &sum, double &sumsq, float &mn,
+                                           float &mx)
+{
+    const int ostep = rpp * width, sstep = rpp * cols;
+    orow += r_off * width;
+    src += r_off * cols;
+    for (int r = r_off; r < nout; r += rpp, orow += ostep, src += sstep) {
+        const float sval = *src;
+        // Q1 shifts only what is WRITTEN for the flushed rows; the reference takes its statistics on the first
+        // block's own statics (mfcccpu.cpp:274 / :383-384), i.e. always un-shifted
+        *orow = r >= rq ? src[-D * cols] : sval;
+        if (KIND >= 1 && r < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
+            sum += (double)sval;
+            if (KIND >= 2) sumsq += (double)__fmul_rn(sval, sval);
+            if (KIND >= 3) { mn = fminf(mn, sval); mx = fmaxf(mx, sval); }
+        }
+    }
+}
+
+} // namespace dev
+
 template <int N2, int NZ, bool FAST, int kFusedWarps>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
@@ -193,9 +233,9 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     }
     dev::LaneConsts<N2, NZ> lc;
     dev::load_lane_consts<N2, NZ>(lc, a.window2, a.tw_a, a.tw_p, lf);
-    // phase 2 reads whole 4-bin chunks: up to 3 floats past a filter's end, i.e. into the next row (or the pad) with a
+    // phase 2 reads whole 8-bin chunks: up to 7 floats past a filter's end, i.e. into the next row (or the pad) with a
     // ZERO weight. Rows of frames that are never computed (short tiles) must therefore hold finite numbers.
-    for (int i = tid; i < kRoundFrames * BINS + 4; i += kFusedThreads) s_mags[i] = 0.f;
+    for (int i = tid; i < kRoundFrames * BINS + 8; i += kFusedThreads) s_mags[i] = 0.f;
     __syncthreads();
 
     uint32_t parity = 0;
@@ -228,7 +268,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 const int fr = warp * kWarpFrames + fl;          // frame within the round
                 const int row = (fr >> 1) + 16 * (fr & 1);       // magnitude row (see header)
                 const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
-                dev::fft_frame_mag<N2, NZ, true>(words, lc, w_scratch + fw * SCR, s_mags + row * BINS, lf);
+                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + row * BINS, lf);
             }
             // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
             if (a.use_tma && lane == 0 && r + 1 < nrounds) issue_tma(r + 1);
@@ -242,17 +282,17 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
 #pragma unroll
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
             for (int b = warp; b < a.nb; b += kFusedWarps) {
-                const int n4 = mc.n4[b];
+                const int n8 = mc.n8[b];
                 const float4 *wv = mc.wl4 + mc.woff4[b];
                 const float *mv = mrow + mc.fstart[b];
                 float acc = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < n4; i++) { // ascending bins, like the reference sweep
-                    const float4 w = wv[i];
-                    acc = fmaf(w.x, mv[4 * i + 0], acc);
-                    acc = fmaf(w.y, mv[4 * i + 1], acc);
-                    acc = fmaf(w.z, mv[4 * i + 2], acc);
-                    acc = fmaf(w.w, mv[4 * i + 3], acc);
+#pragma unroll 1
+                for (int i = 0; i < n8; i++, wv += 2, mv += 8) { // ascending bins, like the reference sweep
+                    const float4 w0 = wv[0], w1 = wv[1];
+                    acc = fmaf(w0.x, mv[0], acc); acc = fmaf(w0.y, mv[1], acc);
+                    acc = fmaf(w0.z, mv[2], acc); acc = fmaf(w0.w, mv[3], acc);
+                    acc = fmaf(w1.x, mv[4], acc); acc = fmaf(w1.y, mv[5], acc);
+                    acc = fmaf(w1.z, mv[6], acc); acc = fmaf(w1.w, mv[7], acc);
                 }
                 const float e = dev::mel_log<FAST>(acc);
                 if (a.dct_len > 0) {
@@ -305,25 +345,25 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         if (rl < rp) {
             for (int i = rl; i < nd; i += rp) {
                 const int u = t0 - l2 + i;
-                float num = 0.f;
-                for (int l = 1; l <= l1; l++) {
-                    const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
-                    const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
-                    num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
+                float num;
+                if (u - l1 >= 0 && u + l1 <= T - 1) // interior: no edge replication needed
+                    num = dev::delta_num(s_cep + (u - c0f) * cols + c, cols, l1);
+                else {
+                    num = 0.f;
+                    for (int l = 1; l <= l1; l++) {
+                        const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
+                        const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
+                        num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
+                    }
                 }
                 s_dhat[i * cols + c] = num * a.rden1;
             }
         }
         __syncthreads();
         if (a.nstreams >= 3) { // 3b: delta-delta of the extended delta rows
-            if (rl < rp) {
-                for (int r = rl; r < nout; r += rp) {
-                    const float *dc = s_dhat + (r + l2) * cols + c;
-                    float num = 0.f;
-                    for (int l = 1; l <= l2; l++) num = fmaf((float)l, dc[l * cols] - dc[-l * cols], num);
-                    s_dd[r * cols + c] = num * a.rden2;
-                }
-            }
+            if (rl < rp)
+                for (int r = rl; r < nout; r += rp)
+                    s_dd[r * cols + c] = dev::delta_num(s_dhat + (r + l2) * cols + c, cols, l2) * a.rden2;
             __syncthreads();
         }
     }
@@ -343,16 +383,11 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     float mn = FLT_MAX, mx = -FLT_MAX;
     if (active) {
         float *orow = a.out + (tl.out_row0 + t0) * (long long)width + col;
-        for (int r = r_off; r < nout; r += rpp) {
-            const float sval = src[r * cols];
-            // Q1 shifts only what is WRITTEN for the flushed rows; the reference takes its statistics on the first
-            // block's own statics (mfcccpu.cpp:274 / :383-384), i.e. always un-shifted
-            orow[(long long)r * width] = r >= rq ? src[(r - D) * cols] : sval;
-            if (r < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
-                if (a.stats_kind >= 1) sum += (double)sval;
-                if (a.stats_kind >= 2) sumsq += (double)__fmul_rn(sval, sval);
-                if (a.stats_kind >= 3) { mn = fminf(mn, sval); mx = fmaxf(mx, sval); }
-            }
+        switch (a.stats_kind) {
+        case 0: dev::write_rows<0>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+        case 1: dev::write_rows<1>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+        case 2: dev::write_rows<2>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+        default: dev::write_rows<3>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
         }
     }
     if (a.partials) {
