@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libafe_cuda.so")
 NORM_NONE, NORM_CMN, NORM_CVN, NORM_MINMAX = 0, 1, 2, 3
 DYN_NONE, DYN_DELTA, DYN_ACC = 0, 1, 2
 STATS_REFERENCE_BLOCK, STATS_UTTERANCE, STATS_CORPUS = 0, 1, 2
-BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH = 1, 2, 4
+BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM = 1, 2, 4, 8
 OPT_FIX_FLUSH_STATICS = 1
 
 # every symbol include/afe_cuda.h declares (tests/test_abi.py checks the header against this list and the .so)

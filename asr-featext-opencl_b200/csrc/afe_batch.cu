@@ -184,6 +184,7 @@ struct afe_batch {
     Tile *d_tiles = nullptr;
     int *d_tile_begin = nullptr;
     double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr, *d_scratch = nullptr;
+    int *d_counters = nullptr;
     int *d_scratch_begin = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
@@ -205,6 +206,8 @@ struct afe_batch {
         if (d_partials) cudaFree(d_partials);
         if (d_stats) cudaFree(d_stats);
         if (d_scratch) cudaFree(d_scratch);
+        if (d_counters) cudaFree(d_counters);
+        d_counters = nullptr;
         if (d_scratch_begin) cudaFree(d_scratch_begin);
         d_scratch = nullptr; d_scratch_begin = nullptr;
         if (d_mean) cudaFree(d_mean);
@@ -257,13 +260,15 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
 }
 
 template <int N2, int NZ, int WARPS>
-static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1)
+static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm)
 {
     const Derived &d = b->d;
     FusedArgs a{};
-    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles + t0;
+    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles; a.tile_base = t0;
     a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.partials = want_stats ? b->d_partials + (size_t)t0 * d.width * 4 : nullptr;
+    a.partials = want_stats ? b->d_partials : nullptr;
+    a.counters = (want_stats && fuse_norm) ? b->d_counters : nullptr;
+    a.norm_type = d.p.norm; a.norm_after_dyn = d.p.norm_after_dyn;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
     a.q1 = (b->flags & AFE_BATCH_Q1_EXACT) && d.D > 0 ? 1 : 0;
@@ -287,7 +292,7 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     b->last_launches++;
 }
 
-static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1)
+static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1, bool fuse_norm = false)
 {
     if (t1 < 0) t1 = b->n_tiles;
     if (t1 <= t0) return;
@@ -299,14 +304,14 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
     const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->warps == 8 ? 1 : 0);
     switch (key) {
-    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1); break;
-    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1); break;
+    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
     }
 }
 
@@ -469,6 +474,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
                 Tile tl;
                 tl.pcm_off = off[u]; tl.out_row0 = b->frame_off[u]; tl.T = T; tl.t0 = t0;
                 tl.nout = std::min(nout, T - t0); tl.group = corpus ? 0 : u;
+                tl.tile0 = b->h_tile_begin[u]; tl.ntiles = (T + nout - 1) / nout;
                 tiles.push_back(tl);
             }
             const double cnt = !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
@@ -498,6 +504,8 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
                 AFE_CUDA(cudaMalloc(&b->d_scratch_begin, sizeof(sb)));
                 AFE_CUDA(cudaMemcpy(b->d_scratch_begin, sb, sizeof(sb), cudaMemcpyHostToDevice));
             }
+            AFE_CUDA(cudaMalloc(&b->d_counters, sizeof(int) * b->n_groups));
+            AFE_CUDA(cudaMemset(b->d_counters, 0, sizeof(int) * b->n_groups));
             AFE_CUDA(cudaMalloc(&b->d_mean, sizeof(float) * w * b->n_groups));
             AFE_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * w * b->n_groups));
         }
@@ -525,8 +533,9 @@ int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
         if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
             throw Error("corpus statistics need the two-pass sequence: extract_device, corpus_stats, allreduce, normalize_device");
         b->last_launches = 0;
-        run_extract(b, d_pcm, d_out);
-        if (b->d.p.norm != AFE_NORM_NONE) { run_reduce(b); run_normalize(b, d_out); }
+        const bool fuse = !(b->flags & AFE_BATCH_UNFUSED_NORM);
+        run_extract(b, d_pcm, d_out, 0, -1, fuse);   // per-utterance scopes: the last tile of an utterance normalises it
+        if (b->d.p.norm != AFE_NORM_NONE && !fuse) { run_reduce(b); run_normalize(b, d_out); }
     });
 }
 
@@ -625,8 +634,9 @@ int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
             AFE_CUDA(cudaEventRecord(b->ev_in[c], b->s_in));
             AFE_CUDA(cudaStreamWaitEvent(b->stream, b->ev_in[c], 0));
             const int t0 = b->h_tile_begin[u0], t1 = b->h_tile_begin[u1];
-            run_extract(b, b->d_pcm_stage, b->d_out_stage, t0, t1);
-            if (norm) { run_reduce(b, u0, u1); run_normalize(b, b->d_out_stage, t0, t1, u0, u1); }
+            const bool fuse = !(b->flags & AFE_BATCH_UNFUSED_NORM);
+            run_extract(b, b->d_pcm_stage, b->d_out_stage, t0, t1, fuse);
+            if (norm && !fuse) { run_reduce(b, u0, u1); run_normalize(b, b->d_out_stage, t0, t1, u0, u1); }
             AFE_CUDA(cudaEventRecord(b->ev_k[c], b->stream));
             AFE_CUDA(cudaStreamWaitEvent(b->s_out, b->ev_k[c], 0));
             const size_t r0 = (size_t)b->frame_off[u0] * d.width, r1 = (size_t)b->frame_off[u1] * d.width;

@@ -35,6 +35,8 @@ struct Tile {
     int t0;              // first output frame of this tile
     int nout;            // output frames of this tile
     int group;           // statistics group (utterance index, or 0 for corpus scope)
+    int tile0;           // index of the utterance's first tile
+    int ntiles;          // tiles of the utterance
 };
 
 constexpr int kMaxBanks = 64;
@@ -56,7 +58,10 @@ struct FusedArgs {
     float *out;
     const Tile *tiles;
     const float2 *window2, *tw_a, *tw_p;
-    double *partials;    // [ntiles][width][4] or nullptr
+    double *partials;    // [ntiles][width][4] or nullptr (indexed by absolute tile number)
+    int *counters;       // [groups] arrival tickets for the fused normalisation (self-resetting), or nullptr
+    int tile_base;       // absolute index of this launch's first tile
+    int norm_type, norm_after_dyn;
     int W, S, nb, dct_len, cols, width, l1, l2, nstreams;
     int q1;              // reproduce the single-block flush quirk
     int use_tma;
@@ -210,7 +215,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     unsigned char *w_pcm = wbase + L.w_pcm;
     float2 *w_scratch = reinterpret_cast<float2 *>(smem + L.off_part + warp * L.w_scratch); // aliased by s_part in phase 2
 
-    const Tile tl = a.tiles[blockIdx.x];
+    const int tile_idx = a.tile_base + blockIdx.x;
+    const Tile tl = a.tiles[tile_idx];
     const int D = a.l1 + a.l2, cols = a.cols;
     const int c0f = max(0, tl.t0 - D), c1f = min(tl.T, tl.t0 + tl.nout + D);
     const int ncomp = c1f - c0f;
@@ -403,8 +409,61 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 s0 += p[0]; s1 += p[1];
                 lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
             }
-            double *dst = a.partials + ((long long)blockIdx.x * width + tid) * 4;
+            double *dst = a.partials + ((long long)tile_idx * width + tid) * 4;
             dst[0] = s0; dst[1] = s1; dst[2] = lo; dst[3] = hi;
+        }
+    }
+
+    // ---- fused normalisation (per-utterance statistics scopes): the LAST tile of an utterance to finish reduces the
+    //      utterance's per-tile partials in tile order (deterministic, whoever is last), finalises mean / scale
+    //      (normalizercpu.cpp:31-66) and normalises the utterance's rows in place while they are still L2 resident.
+    //      Replaces K2 + K3 (three launches and one extra HBM round trip of the features).
+    if (a.counters) {
+        __shared__ int s_last;
+        float *s_mean = reinterpret_cast<float *>(smem + L.off_dhat), *s_scale = s_mean + width;
+        __threadfence(); // rows + partial record of this tile are visible device-wide before the ticket is taken
+        __syncthreads();
+        if (tid == 0) {
+            const int ticket = atomicAdd(a.counters + tl.group, 1);
+            s_last = ticket == tl.ntiles - 1;
+            if (s_last) a.counters[tl.group] = 0; // ready for the next launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (tid < width) {
+                const int src_col = a.norm_after_dyn ? tid : tid % cols;
+                double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+                for (int t = 0; t < tl.ntiles; t++) {
+                    const double *p = a.partials + ((long long)(tl.tile0 + t) * width + src_col) * 4;
+                    s0 += __ldcg(p); s1 += __ldcg(p + 1);
+                    lo = fmin(lo, __ldcg(p + 2)); hi = fmax(hi, __ldcg(p + 3));
+                }
+                const double n = (double)n_stats;
+                float m = (float)(s0 / n), sc = 1.f;
+                if (a.norm_type == AFE_NORM_CVN) sc = (float)sqrt((n - 1.0) / (s1 - s0 * (s0 / n)));
+                else if (a.norm_type == AFE_NORM_MINMAX) sc = 1.f / fmaxf(fabsf((float)lo - m), fabsf((float)hi - m));
+                if (!a.norm_after_dyn && tid >= cols) m = 0.f;
+                s_mean[tid] = m; s_scale[tid] = sc;
+            }
+            __syncthreads();
+            if (active) { // same (row group, column) ownership as the row writer: no division in the loop
+                float *o = a.out + tl.out_row0 * (long long)width + col;
+                const float m = s_mean[col], sc = a.norm_type == AFE_NORM_CMN ? 1.f : s_scale[col];
+                const bool cmn = a.norm_type == AFE_NORM_CMN;
+                const int step = rpp * width;
+                o += r_off * width;
+                int r = r_off;
+                constexpr int U = 8; // loads in flight per thread: the rows come from L2, ~300 cycles away
+                for (; r + (U - 1) * rpp < T; r += U * rpp, o += U * step) {
+                    float v[U];
+#pragma unroll
+                    for (int k = 0; k < U; k++) v[k] = __ldcg(o + k * step);
+#pragma unroll
+                    for (int k = 0; k < U; k++) o[k * step] = cmn ? v[k] - m : (v[k] - m) * sc;
+                }
+                for (; r < T; r += rpp, o += step) *o = cmn ? __ldcg(o) - m : (__ldcg(o) - m) * sc;
+            }
         }
     }
 }

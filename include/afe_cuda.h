@@ -150,7 +150,8 @@ enum afe_stats_scope {
 enum afe_batch_flags {
     AFE_BATCH_Q1_EXACT = 1,        /* reproduce the single-block flush quirk Q1 (statics of the last D rows) */
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
-    AFE_BATCH_FAST_MATH = 4        /* MUFU log2/sqrt approximations in the fused kernel (tolerance-checked in tests) */
+    AFE_BATCH_FAST_MATH = 4,       /* MUFU log2 approximation in the fused kernel (tolerance-checked in tests) */
+    AFE_BATCH_UNFUSED_NORM = 8     /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
 };
 
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out);

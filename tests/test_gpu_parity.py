@@ -172,7 +172,7 @@ def test_normalizer_cuda(oracle, norm):
 SOUNDFILES = ["a0001", "a1", "a2", "a3", "a4", "a5"]
 
 
-@pytest.mark.parametrize("flags", [0, afe.BATCH_NO_TMA], ids=["tma", "plain-loads"])
+@pytest.mark.parametrize("flags", [0, afe.BATCH_NO_TMA, afe.BATCH_UNFUSED_NORM], ids=["tma", "plain-loads", "unfused-norm"])
 def test_batch_config2_soundfiles_q1_exact(oracle, flags):
     """BASELINE config 2: a0001 + a1..a5, 23 mel, 12+c0, delta+delta-delta, per-utterance CMN, one block per
     utterance. AFE_BATCH_Q1_EXACT == the reference driver with its default sample_limit (single set_input + flush)."""
@@ -201,6 +201,15 @@ def test_batch_config2_intended_semantics(oracle):
     want = oracle_extract(oracle, p, utts, 0)
     for n, g, w in zip(SOUNDFILES, got, want):
         assert_close(g, w, p, n)
+
+
+def test_batch_unfused_variants(oracle):
+    """K2 + K3 kernels (AFE_BATCH_UNFUSED_NORM) for CVN / MINMAX / norm-before-dyn."""
+    G = load_golden()
+    for case in ("v_a1_cvn", "v_a1_minmax", "v_a1_norm_before_dyn"):
+        g = G[case]
+        got = run_batch(g["params"], [load_pcm()[g["utt"]]], flags=afe.BATCH_Q1_EXACT | afe.BATCH_UNFUSED_NORM)[0]
+        assert_close(got[g["rows"]], g["feats"], g["params"], case + " unfused")
 
 
 @pytest.mark.parametrize("case", ["c1_sample1", "c1_sample1_acc", "c3_a1_40mel", "c3_a1_40mel_nonorm", "v_a1_cvn",
@@ -274,10 +283,12 @@ def test_batch_is_deterministic_and_order_independent():
     b = run_batch(p, utts)
     c = run_batch(p, utts[::-1])[::-1]
     d = run_batch(p, utts, flags=afe.BATCH_NO_TMA)
+    e = run_batch(p, utts, flags=afe.BATCH_UNFUSED_NORM)   # separate K2/K3 kernels == in-kernel normalisation, bitwise
     for i in range(len(utts)):
         np.testing.assert_array_equal(a[i], b[i])
         np.testing.assert_array_equal(a[i], c[i])
         np.testing.assert_array_equal(a[i], d[i])
+        np.testing.assert_array_equal(a[i], e[i])
 
 
 def test_batch_linearity_property():
