@@ -48,7 +48,8 @@ def workload_config(n_utts, n_gpus):
             "utterances_per_gpu": n_utts, "samples_per_utterance": SR * SECONDS,
             "frames_per_gpu": n_utts * ((SR * SECONDS - (W - S)) // S),
             "sharding": f"utterance-sharded x{n_gpus}, no data-path collective",
-            "l2_policy": "inputs (3.2 GB PCM per GPU) are larger than L2 (126 MB); no explicit flush"}
+            "l2_policy": f"inputs ({n_utts * SR * SECONDS * 2 / 1e9:.2f} GB PCM + {n_utts * ((SR * SECONDS - (W - S)) // S) * WIDTH * 4 / 1e9:.2f} GB "
+                         "features per GPU) are larger than L2 (126 MB); no explicit flush"}
 
 
 def synth_host(n_utts, seed):
