@@ -429,10 +429,10 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
         const char *env_w = getenv("AFE_FUSED_WARPS");
         if (env_w) b->warps = atoi(env_w) == 4 ? 4 : 8;
-        // tile geometry: the cepstra tile holds up to 352 frames (<= 4.6 K floats of shared memory)
+        // tile geometry: the cepstra tile holds up to 512 frames (<= 6.9 K floats of shared memory)
         const char *env_tc = getenv("AFE_TILE_FRAMES");
-        int tc = env_tc ? atoi(env_tc) : 352;
-        tc = std::min(tc, (4608 / d.cols) / kRoundFrames * kRoundFrames);
+        int tc = env_tc ? atoi(env_tc) : 512;
+        tc = std::min(tc, (6912 / d.cols) / kRoundFrames * kRoundFrames); // cepstra tile <= 27 KB: still 2 CTAs per SM
         tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
         b->tc_max = tc; b->nout_max = tc - 2 * d.D;
         b->n_utts = n_utts;
