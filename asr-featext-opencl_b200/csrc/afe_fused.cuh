@@ -291,15 +291,16 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 const int n8 = mc.n8[b];
                 const float4 *wv = mc.wl4 + mc.woff4[b];
                 const float *mv = mrow + mc.fstart[b];
-                float acc = 0.f;
+                float acc = 0.f, acc1 = 0.f; // two chains (bins 0-3 / 4-7 of every chunk) for instruction-level parallelism
 #pragma unroll 1
-                for (int i = 0; i < n8; i++, wv += 2, mv += 8) { // ascending bins, like the reference sweep
+                for (int i = 0; i < n8; i++, wv += 2, mv += 8) { // ascending bins within each chain
                     const float4 w0 = wv[0], w1 = wv[1];
-                    acc = fmaf(w0.x, mv[0], acc); acc = fmaf(w0.y, mv[1], acc);
-                    acc = fmaf(w0.z, mv[2], acc); acc = fmaf(w0.w, mv[3], acc);
-                    acc = fmaf(w1.x, mv[4], acc); acc = fmaf(w1.y, mv[5], acc);
-                    acc = fmaf(w1.z, mv[6], acc); acc = fmaf(w1.w, mv[7], acc);
+                    acc = fmaf(w0.x, mv[0], acc); acc1 = fmaf(w1.x, mv[4], acc1);
+                    acc = fmaf(w0.y, mv[1], acc); acc1 = fmaf(w1.y, mv[5], acc1);
+                    acc = fmaf(w0.z, mv[2], acc); acc1 = fmaf(w1.z, mv[6], acc1);
+                    acc = fmaf(w0.w, mv[3], acc); acc1 = fmaf(w1.w, mv[7], acc1);
                 }
+                acc += acc1;
                 const float e = dev::mel_log<FAST>(acc);
                 if (a.dct_len > 0) {
 #pragma unroll
