@@ -245,11 +245,12 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     int off4 = 0;
     const float scale = 0.5f / (float)d.N2; // the kernel stores |2X|; scaling by a power of two commutes with rounding
     for (int b = 0; b < d.nb; b++) {
-        const int j0 = edges[b], n = edges[b + 2] - edges[b], n8 = (n + 7) / 8;
+        const int j0 = edges[b], j1 = edges[b + 2], s4 = j0 & ~3, n8 = std::max(1, (j1 - s4 + 7) / 8);
         if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
-        mc.fstart[b] = (short)j0; mc.n8[b] = (short)n8; mc.woff4[b] = (short)off4;
+        if (s4 + 8 * n8 > kMagStride + 16) throw Error("mel filter too wide for the fused kernel");
+        mc.fchunk[b] = (short)(s4 / 4); mc.n8[b] = (short)n8; mc.woff4[b] = (short)off4;
         float *w = reinterpret_cast<float *>(mc.wl4 + off4);
-        for (int j = 0; j < n; j++) w[j] = filters[(size_t)(b % 2) * d.N2 + j0 + j] * scale;
+        for (int j = j0; j < j1; j++) w[j - s4] = filters[(size_t)(b % 2) * d.N2 + j] * scale;
         off4 += 2 * n8;
     }
     if (d.C > 0) {
@@ -278,6 +279,7 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
     a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
     a.tc_max = b->tc_max;
+    { const char *dbg = getenv("AFE_DEBUG_SKIP"); a.debug_skip = dbg ? atoi(dbg) : 0; }
     float den1 = 0, den2 = 0;
     for (int l = 1; l <= d.l1; l++) den1 += l * l;   // float accumulation like deltacpu.cpp:26
     for (int l = 1; l <= d.l2; l++) den2 += l * l;

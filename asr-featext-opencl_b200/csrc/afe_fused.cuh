@@ -6,9 +6,10 @@
 // mfcccpu.cpp:243-254) in rounds of 32 frames:
 //   stage 0  each warp stages the PCM of ITS 8 frames with one cp.async.bulk (TMA, SASS UBLKCP) into its own buffer,
 //            completion on its own mbarrier; the next round's copy is issued as soon as this round's FFTs are done
-//   phase 1  each warp: 8/FPW calls of the in-register FFT + magnitude (afe_fft.cuh) -> mags[32][257] (CTA shared);
-//            frame f lives in row (f>>1) + 16*(f&1): the two adjacent frames of one call land 16 banks apart AND
-//            phase 2's "lane = frame" reads of one bin hit 32 different banks
+//   phase 1  each warp: 32/(WARPS*FPW) calls of the in-register FFT + magnitude (afe_fft.cuh) -> mags[32][260] (CTA
+//            shared). Frame f lives in row mag_row(f): the two adjacent frames of one call land 4 rows = 16 banks
+//            apart, and the 8 frames of a quarter warp occupy 8 consecutive rows, so phase 2's "lane = frame" 128-bit
+//            reads (row stride 65 chunks = 1 mod 8) are conflict free
 //   phase 2  mel + log + DCT, ONE THREAD PER FRAME, warp w owning the filters b = w (mod 4). The triangular weights and
 //            the DCT matrix are kernel parameters, i.e. constant-bank operands: they cost no shared-memory bandwidth,
 //            which is what bounds this kernel (v3/v4 re-loaded weights per lane: 116 of 245 smem wavefronts per frame,
@@ -40,16 +41,20 @@ struct Tile {
 };
 
 constexpr int kMaxBanks = 64;
-constexpr int kMaxWl4 = (2 * 257 + 7 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists padded to 8
+constexpr int kMaxWl4 = (2 * 257 + 10 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists start on a
+                                                            // multiple of 4 bins and are padded to whole 8-bin chunks
+constexpr int kMagStride = 260; // floats per magnitude row (16-byte aligned rows)
+// row of frame f (0..31) of a round: pair k = f>>1 -> rows 8*(k>>2) + (k&3) and +4
+__host__ __device__ constexpr int mag_row(int f) { return 8 * (f >> 3) + ((f >> 1) & 3) + 4 * (f & 1); }
 
 // Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only,
 // read with 128-bit constant loads. Weight lists are zero padded to a multiple of 4 bins; DCT rows to 16 columns.
 struct MelConst {
-    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + 2*n8[b]), bins fstart[b] + 8*i + {0..7}; the weights
+    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + 2*n8[b]), bins 4*fchunk[b] + 8*i + {0..7}; the weights
                                  // carry the 0.5/N2 magnitude scale (an exact power of two), see fft_frame_mag
     float4 dct4[kMaxBanks][4];   // [nb][16]
-    short fstart[kMaxBanks];     // first bin of filter b  (= edges[b])
-    short n8[kMaxBanks];         // 8-bin chunks of filter b (= ceil((edges[b+2]-edges[b]) / 8))
+    short fchunk[kMaxBanks];     // first 4-bin chunk of filter b (= edges[b] / 4; leading weights are zero)
+    short n8[kMaxBanks];         // 8-bin chunks of filter b
     short woff4[kMaxBanks];
 };
 
@@ -62,6 +67,7 @@ struct FusedArgs {
     int *counters;       // [groups] arrival tickets for the fused normalisation (self-resetting), or nullptr
     int tile_base;       // absolute index of this launch's first tile
     int norm_type, norm_after_dyn;
+    int debug_skip;      // timing experiments only (AFE_DEBUG_SKIP): 1 skip FFT calls, 2 skip mel/DCT, 4 skip phase 3 + normalise
     int W, S, nb, dct_len, cols, width, l1, l2, nstreams;
     int q1;              // reproduce the single-block flush quirk
     int use_tma;
@@ -89,7 +95,7 @@ FusedSmem fused_smem_layout(int kFusedWarps, int S, int cols, int tc_max, int no
     FusedSmem L;
     int o = 0;
     L.off_mbar = o; o += align_up(kFusedWarps * 8, 16);           // one mbarrier per warp, never aliased
-    L.off_mags = o; o += align_up((kRoundFrames * C::BINS + 8) * 4, 16); // [32][M+1] + pad for whole-chunk reads
+    L.off_mags = o; o += align_up((kRoundFrames * kMagStride + 16) * 4, 16); // [32][260] + pad for whole-chunk reads
     // per-warp staging [pcm]; then the FFT exchange tiles [scratch], which phase 2 reuses for the partial cepstra
     L.pcm_bytes = align_up(((kWarpFrames - 1) * S + N2) * 2, 16) + 16;
     L.w_pcm = 0;
@@ -200,7 +206,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
 {
     using C = dev::FftCfg<N2>;
     constexpr int kFusedThreads = 32 * kFusedWarps, kWarpFrames = kRoundFrames / kFusedWarps;
-    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR, BINS = C::BINS;
+    constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR;
     static_assert(kWarpFrames % FPW == 0, "a warp's frames must fill whole FFT calls");
     extern __shared__ __align__(128) unsigned char smem[];
     float *s_mags = reinterpret_cast<float *>(smem + L.off_mags);
@@ -239,9 +245,9 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     }
     dev::LaneConsts<N2, NZ> lc;
     dev::load_lane_consts<N2, NZ>(lc, a.window2, a.tw_a, a.tw_p, lf);
-    // phase 2 reads whole 8-bin chunks: up to 7 floats past a filter's end, i.e. into the next row (or the pad) with a
+    // phase 2 reads whole 8-bin chunks: up to 11 floats past a filter's end, i.e. into the next row (or the pad) with a
     // ZERO weight. Rows of frames that are never computed (short tiles) must therefore hold finite numbers.
-    for (int i = tid; i < kRoundFrames * BINS + 8; i += kFusedThreads) s_mags[i] = 0.f;
+    for (int i = tid; i < kRoundFrames * kMagStride + 16; i += kFusedThreads) s_mags[i] = 0.f;
     __syncthreads();
 
     uint32_t parity = 0;
@@ -269,12 +275,11 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 __syncwarp();
             }
 #pragma unroll 1
-            for (int it = 0; it * FPW < nfw; it++) {
+            for (int it = 0; it * FPW < nfw && !(a.debug_skip & 1); it++) {
                 const int fl = it * FPW + fw;                    // frame within the warp's 8 (adjacent frames per call)
                 const int fr = warp * kWarpFrames + fl;          // frame within the round
-                const int row = (fr >> 1) + 16 * (fr & 1);       // magnitude row (see header)
                 const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
-                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + row * BINS, lf);
+                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + mag_row(fr) * kMagStride, lf);
             }
             // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
             if (a.use_tma && lane == 0 && r + 1 < nrounds) issue_tma(r + 1);
@@ -282,23 +287,24 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         __syncthreads(); // A: all magnitudes of the round are in shared memory
 
         // ---- phase 2: lane = frame of the round, warp = filter class
-        if (lane < nfr) {
-            const float *mrow = s_mags + ((lane >> 1) + 16 * (lane & 1)) * BINS;
+        if (lane < nfr && !(a.debug_skip & 2)) {
+            const float4 *mrow = reinterpret_cast<const float4 *>(s_mags + mag_row(lane) * kMagStride);
             float cep[16];
 #pragma unroll
             for (int c = 0; c < 16; c++) cep[c] = 0.f;
             for (int b = warp; b < a.nb; b += kFusedWarps) {
                 const int n8 = mc.n8[b];
                 const float4 *wv = mc.wl4 + mc.woff4[b];
-                const float *mv = mrow + mc.fstart[b];
+                const float4 *mv = mrow + mc.fchunk[b];
                 float acc = 0.f, acc1 = 0.f; // two chains (bins 0-3 / 4-7 of every chunk) for instruction-level parallelism
-#pragma unroll 1
-                for (int i = 0; i < n8; i++, wv += 2, mv += 8) { // ascending bins within each chain
-                    const float4 w0 = wv[0], w1 = wv[1];
-                    acc = fmaf(w0.x, mv[0], acc); acc1 = fmaf(w1.x, mv[4], acc1);
-                    acc = fmaf(w0.y, mv[1], acc); acc1 = fmaf(w1.y, mv[5], acc1);
-                    acc = fmaf(w0.z, mv[2], acc); acc1 = fmaf(w1.z, mv[6], acc1);
-                    acc = fmaf(w0.w, mv[3], acc); acc1 = fmaf(w1.w, mv[7], acc1);
+#pragma unroll 2
+                for (int i = 0; i < n8; i++) { // ascending bins within each chain
+                    const float4 w0 = wv[2 * i], w1 = wv[2 * i + 1];
+                    const float4 m0 = mv[2 * i], m1 = mv[2 * i + 1];
+                    acc = fmaf(w0.x, m0.x, acc); acc1 = fmaf(w1.x, m1.x, acc1);
+                    acc = fmaf(w0.y, m0.y, acc); acc1 = fmaf(w1.y, m1.y, acc1);
+                    acc = fmaf(w0.z, m0.z, acc); acc1 = fmaf(w1.z, m1.z, acc1);
+                    acc = fmaf(w0.w, m0.w, acc); acc1 = fmaf(w1.w, m1.w, acc1);
                 }
                 acc += acc1;
                 const float e = dev::mel_log<FAST>(acc);
@@ -345,6 +351,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     float *s_dd = reinterpret_cast<float *>(smem + L.off_dd);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;
+    if (a.debug_skip & 4) return;
     if (a.nstreams >= 2) {
         // 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
         const int rp = kFusedThreads / cols, rl = tid / cols, c = tid - rl * cols;
