@@ -455,7 +455,9 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             b->pcm_extent = std::max<int64_t>(b->pcm_extent, off[u] + n);
             if (off[u] % 2) throw Error("plan: utterance offsets must be even (32-bit PCM word loads)");
             if (off[u] % 8) aligned = false;
-            const int T = afe_estimated_window_count((int)n, d.W, d.S);
+            // parambase.cpp:16-19 evaluates in float32, which is inexact above 2^24 samples: never let it exceed the
+            // exact count (the extra frame would lie outside the utterance)
+            const int T = std::min(afe_estimated_window_count((int)n, d.W, d.S), (int)std::max<int64_t>(0, (n - (d.W - d.S)) / d.S));
             if (T <= 2 * d.D || T < 1) throw Error("Can't process data, window count is too small"); // segmentercpu.cpp:65-66
             b->frame_off[u + 1] = b->frame_off[u] + T;
             // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
