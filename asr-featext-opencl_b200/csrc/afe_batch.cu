@@ -93,7 +93,8 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, const int
     const int g = blockIdx.x, c = threadIdx.x;
     if (c >= width) return;
     double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
-    for (int t = tile_begin[g]; t < tile_begin[g + 1]; t++) { // fixed order: deterministic
+#pragma unroll 8
+    for (int t = tile_begin[g]; t < tile_begin[g + 1]; t++) { // fixed order: deterministic (loads are hoisted, adds stay ordered)
         const double *p = partials + ((long long)t * width + c) * 4;
         s0 += p[0]; s1 += p[1];
         lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
