@@ -210,7 +210,6 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     static_assert(kWarpFrames % FPW == 0, "a warp's frames must fill whole FFT calls");
     extern __shared__ __align__(128) unsigned char smem[];
     float *s_mags = reinterpret_cast<float *>(smem + L.off_mags);
-    float4 *s_part = reinterpret_cast<float4 *>(smem + L.off_part);
     float *s_cep = reinterpret_cast<float *>(smem + L.off_cep);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -286,64 +285,87 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         }
         __syncthreads(); // A: all magnitudes of the round are in shared memory
 
-        // ---- phase 2: lane = frame of the round, warp = filter class
+        // ---- phase 2: lane = frame of the round, warp = filter class (filters warp, warp + WARPS, ...).
+        //      Three unrolled passes over the warp's <= KF filters - sums, logs, DCT - so that the independent filters'
+        //      long dependency chains (accumulation, logf) interleave instead of running back to back.
         if (lane < nfr && !(a.debug_skip & 2)) {
+            constexpr int KF = (kMaxBanks + kFusedWarps - 1) / kFusedWarps;
             const float4 *mrow = reinterpret_cast<const float4 *>(s_mags + mag_row(lane) * kMagStride);
-            float cep[16];
+            float es[KF];
 #pragma unroll
-            for (int c = 0; c < 16; c++) cep[c] = 0.f;
-            for (int b = warp; b < a.nb; b += kFusedWarps) {
-                const int n8 = mc.n8[b];
-                const float4 *wv = mc.wl4 + mc.woff4[b];
-                const float4 *mv = mrow + mc.fchunk[b];
-                float acc = 0.f, acc1 = 0.f; // two chains (bins 0-3 / 4-7 of every chunk) for instruction-level parallelism
+            for (int k = 0; k < KF; k++) {
+                const int b = warp + k * kFusedWarps;
+                float acc = 0.f, acc1 = 0.f; // two chains (bins 0-3 / 4-7 of every chunk), ascending bins within each
+                if (b < a.nb) {              // warp uniform
+                    const int n8 = mc.n8[b];
+                    const float4 *wv = mc.wl4 + mc.woff4[b];
+                    const float4 *mv = mrow + mc.fchunk[b];
 #pragma unroll 2
-                for (int i = 0; i < n8; i++) { // ascending bins within each chain
-                    const float4 w0 = wv[2 * i], w1 = wv[2 * i + 1];
-                    const float4 m0 = mv[2 * i], m1 = mv[2 * i + 1];
-                    acc = fmaf(w0.x, m0.x, acc); acc1 = fmaf(w1.x, m1.x, acc1);
-                    acc = fmaf(w0.y, m0.y, acc); acc1 = fmaf(w1.y, m1.y, acc1);
-                    acc = fmaf(w0.z, m0.z, acc); acc1 = fmaf(w1.z, m1.z, acc1);
-                    acc = fmaf(w0.w, m0.w, acc); acc1 = fmaf(w1.w, m1.w, acc1);
-                }
-                acc += acc1;
-                const float e = dev::mel_log<FAST>(acc);
-                if (a.dct_len > 0) {
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        const float4 d4 = mc.dct4[b][c4];
-                        cep[4 * c4 + 0] = fmaf(e, d4.x, cep[4 * c4 + 0]);
-                        cep[4 * c4 + 1] = fmaf(e, d4.y, cep[4 * c4 + 1]);
-                        cep[4 * c4 + 2] = fmaf(e, d4.z, cep[4 * c4 + 2]);
-                        cep[4 * c4 + 3] = fmaf(e, d4.w, cep[4 * c4 + 3]);
+                    for (int i = 0; i < n8; i++) {
+                        const float4 w0 = wv[2 * i], w1 = wv[2 * i + 1];
+                        const float4 m0 = mv[2 * i], m1 = mv[2 * i + 1];
+                        acc = fmaf(w0.x, m0.x, acc); acc1 = fmaf(w1.x, m1.x, acc1);
+                        acc = fmaf(w0.y, m0.y, acc); acc1 = fmaf(w1.y, m1.y, acc1);
+                        acc = fmaf(w0.z, m0.z, acc); acc1 = fmaf(w1.z, m1.z, acc1);
+                        acc = fmaf(w0.w, m0.w, acc); acc1 = fmaf(w1.w, m1.w, acc1);
                     }
-                } else
-                    s_cep[(f0 + lane) * cols + b] = e;
+                }
+                es[k] = acc + acc1;
             }
+#pragma unroll
+            for (int k = 0; k < KF; k++)
+                if (warp + k * kFusedWarps < a.nb) es[k] = dev::mel_log<FAST>(es[k]);
             if (a.dct_len > 0) {
+                float cep[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) cep[c] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KF; k++) {
+                    const int b = warp + k * kFusedWarps;
+                    if (b < a.nb) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const float4 d4 = mc.dct4[b][c4];
+                            cep[4 * c4 + 0] = fmaf(es[k], d4.x, cep[4 * c4 + 0]);
+                            cep[4 * c4 + 1] = fmaf(es[k], d4.y, cep[4 * c4 + 1]);
+                            cep[4 * c4 + 2] = fmaf(es[k], d4.z, cep[4 * c4 + 2]);
+                            cep[4 * c4 + 3] = fmaf(es[k], d4.w, cep[4 * c4 + 3]);
+                        }
+                    }
+                }
+                // partial cepstra of this filter class -> the exchange tile of the warp that will sum column group c4
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++)
-                    s_part[(warp * 4 + c4) * kRoundFrames + lane] =
+                    reinterpret_cast<float4 *>(smem + L.off_part + c4 * L.w_scratch)[warp * kRoundFrames + lane] =
                         make_float4(cep[4 * c4], cep[4 * c4 + 1], cep[4 * c4 + 2], cep[4 * c4 + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KF; k++)
+                    if (warp + k * kFusedWarps < a.nb) s_cep[(f0 + lane) * cols + warp + k * kFusedWarps] = es[k];
             }
         }
         __syncthreads(); // B: partial cepstra are complete; the magnitudes may be overwritten
-        if (a.dct_len > 0 && lane < nfr && warp < 4) {
-            // warp w (< 4) sums columns 4w..4w+3 of every frame over the filter classes, in a fixed order
-            float4 t = s_part[(0 * 4 + warp) * kRoundFrames + lane];
+        if (a.dct_len > 0 && warp < 4) {
+            // warp w (< 4) sums columns 4w..4w+3 of every frame over the filter classes, in a fixed order. The partials
+            // sit in ITS OWN exchange tile, so no CTA barrier is needed before the next round's FFTs reuse that memory.
+            if (lane < nfr) {
+                const float4 *part = reinterpret_cast<const float4 *>(w_scratch);
+                float4 t = part[lane];
 #pragma unroll
-            for (int w2 = 1; w2 < kFusedWarps; w2++) {
-                const float4 u = s_part[(w2 * 4 + warp) * kRoundFrames + lane];
-                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                for (int w2 = 1; w2 < kFusedWarps; w2++) {
+                    const float4 u = part[w2 * kRoundFrames + lane];
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                float *crow = s_cep + (f0 + lane) * cols + 4 * warp;
+                if (4 * warp + 0 < a.dct_len) crow[0] = t.x;
+                if (4 * warp + 1 < a.dct_len) crow[1] = t.y;
+                if (4 * warp + 2 < a.dct_len) crow[2] = t.z;
+                if (4 * warp + 3 < a.dct_len) crow[3] = t.w;
             }
-            float *crow = s_cep + (f0 + lane) * cols + 4 * warp;
-            if (4 * warp + 0 < a.dct_len) crow[0] = t.x;
-            if (4 * warp + 1 < a.dct_len) crow[1] = t.y;
-            if (4 * warp + 2 < a.dct_len) crow[2] = t.z;
-            if (4 * warp + 3 < a.dct_len) crow[3] = t.w;
+            __syncwarp();
         }
-        __syncthreads(); // C: the partial sums are consumed; their memory is the next round's FFT exchange tile
     }
+    __syncthreads(); // all cepstra of the tile are in shared memory
 
     // ---- phase 3: every thread owns ONE column (c = tid % cols / col = tid % width) and strides over rows, so the loops
     //      are uniform (no integer division, no stream-dependent branch inside them).
