@@ -141,17 +141,46 @@ __global__ void k_finalize_stats(const double *__restrict__ stats, int width, in
     scale[(long long)g * width + c] = sc;
 }
 
+// K3: in-place (x - mean) [* scale] over one tile's rows: 128-bit accesses on the 16-byte aligned body of the tile's
+// contiguous region, columns tracked incrementally (no division in the loop). HBM bound: 8 B per float.
 __global__ void k_normalize_tiles(float *__restrict__ out, const Tile *__restrict__ tiles, int width, int norm_type,
                                   const float *__restrict__ mean, const float *__restrict__ scale)
 {
+    extern __shared__ float s_ms[]; // mean[width] | scale[width]
     const Tile tl = tiles[blockIdx.x];
     float *base = out + (tl.out_row0 + tl.t0) * (long long)width;
-    const float *m = mean + (long long)tl.group * width, *s = scale + (long long)tl.group * width;
     const int n = tl.nout * width;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = i % width;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        s_ms[i] = mean[(long long)tl.group * width + i];
+        s_ms[width + i] = norm_type == AFE_NORM_CMN ? 1.f : scale[(long long)tl.group * width + i];
+    }
+    __syncthreads();
+    const float *m = s_ms, *sc = s_ms + width;
+    const bool cmn = norm_type == AFE_NORM_CMN;
+    const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) >> 2));
+    const int n4 = (n - head) >> 2, tail0 = head + 4 * n4;
+    if ((int)threadIdx.x < head) {
+        const int i = threadIdx.x;
+        const float v = base[i] - m[i % width];
+        base[i] = cmn ? v : v * sc[i % width];
+    }
+    if ((int)threadIdx.x < n - tail0) {
+        const int i = tail0 + threadIdx.x, c = i % width;
         const float v = base[i] - m[c];
-        base[i] = norm_type == AFE_NORM_CMN ? v : v * s[c];
+        base[i] = cmn ? v : v * sc[c];
+    }
+    float4 *p4 = reinterpret_cast<float4 *>(base + head);
+    int c = (head + 4 * (int)threadIdx.x) % width;
+    const int cstep = (4 * (int)blockDim.x) % width;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+        float4 v = p4[j];
+        int c1 = c + 1; if (c1 >= width) c1 -= width;
+        int c2 = c1 + 1; if (c2 >= width) c2 -= width;
+        int c3 = c2 + 1; if (c3 >= width) c3 -= width;
+        v.x -= m[c]; v.y -= m[c1]; v.z -= m[c2]; v.w -= m[c3];
+        if (!cmn) { v.x *= sc[c]; v.y *= sc[c1]; v.z *= sc[c2]; v.w *= sc[c3]; }
+        p4[j] = v;
+        c += cstep; if (c >= width) c -= width;
     }
 }
 
@@ -190,6 +219,10 @@ struct afe_batch {
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
     int warps = 8;            // warps per CTA of the fused kernel (AFE_FUSED_WARPS=4|8)
+    int max_tiles_per_utt = 0;
+    // In-kernel normalisation lets ONE tile normalise its whole utterance: right for short utterances, a serial
+    // bottleneck for a long stream (config 5: 720 tiles) -> those batches take the K2 + K3 kernels.
+    bool fuse_norm() const { return !(flags & AFE_BATCH_UNFUSED_NORM) && max_tiles_per_utt <= 8; }
     FusedSmem L{};
     MelConst mc;
     float mc_alpha = -1.f;
@@ -348,7 +381,8 @@ static void run_normalize(afe_batch *b, float *d_out, int t0 = 0, int t1 = -1, i
                                                       d.p.norm_after_dyn, b->d_mean + g0 * w, b->d_scale + g0 * w);
     AFE_CUDA(cudaGetLastError());
     // Tile::group is absolute, so mean / scale keep their base
-    k_normalize_tiles<<<t1 - t0, 256, 0, b->stream>>>(d_out, b->d_tiles + t0, d.width, d.p.norm, b->d_mean, b->d_scale);
+    k_normalize_tiles<<<t1 - t0, 256, 2 * d.width * sizeof(float), b->stream>>>(d_out, b->d_tiles + t0, d.width, d.p.norm,
+                                                                              b->d_mean, b->d_scale);
     AFE_CUDA(cudaGetLastError());
     count_launch(2); b->last_launches += 2;
 }
@@ -442,6 +476,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->sample_off.assign(off, off + n_utts);
         b->sample_len.assign(len, len + n_utts);
         b->h_tile_begin.assign(n_utts + 1, 0);
+        b->max_tiles_per_utt = 0;
         b->pcm_extent = 0;
         b->frame_off.assign(n_utts + 1, 0);
         std::vector<Tile> tiles;
@@ -474,6 +509,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             }
             const int nout = (T + ntile - 1) / ntile;
             b->h_tile_begin[u] = (int)tiles.size();
+            b->max_tiles_per_utt = std::max(b->max_tiles_per_utt, ntile);
             if (!corpus) tile_begin.push_back((int)tiles.size());
             for (int t0 = 0; t0 < T; t0 += nout) {
                 Tile tl;
@@ -538,7 +574,7 @@ int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
         if (b->scope == AFE_STATS_CORPUS && b->d.p.norm != AFE_NORM_NONE)
             throw Error("corpus statistics need the two-pass sequence: extract_device, corpus_stats, allreduce, normalize_device");
         b->last_launches = 0;
-        const bool fuse = !(b->flags & AFE_BATCH_UNFUSED_NORM);
+        const bool fuse = b->fuse_norm();
         run_extract(b, d_pcm, d_out, 0, -1, fuse);   // per-utterance scopes: the last tile of an utterance normalises it
         if (b->d.p.norm != AFE_NORM_NONE && !fuse) { run_reduce(b); run_normalize(b, d_out); }
     });
@@ -639,7 +675,7 @@ int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
             AFE_CUDA(cudaEventRecord(b->ev_in[c], b->s_in));
             AFE_CUDA(cudaStreamWaitEvent(b->stream, b->ev_in[c], 0));
             const int t0 = b->h_tile_begin[u0], t1 = b->h_tile_begin[u1];
-            const bool fuse = !(b->flags & AFE_BATCH_UNFUSED_NORM);
+            const bool fuse = b->fuse_norm();
             run_extract(b, b->d_pcm_stage, b->d_out_stage, t0, t1, fuse);
             if (norm && !fuse) { run_reduce(b, u0, u1); run_normalize(b, b->d_out_stage, t0, t1, u0, u1); }
             AFE_CUDA(cudaEventRecord(b->ev_k[c], b->stream));
