@@ -7,7 +7,7 @@
 //   twiddle   * exp(-2 pi i n2 k1 / M) from per-lane registers
 //   exchange  one trip through a padded shared-memory tile S[k1][n2] (the only data exchange of the transform)
 //   stage B   R-point FFT over n2 (radix-16, or two radix-8) in registers -> Z[k1 + 16 k2]
-//   split     X[k], X[M-k] from Z[k], Z[M-k] (second trip through the same tile), |X| * 0.5/N2 -> magnitude row
+//   split     X[k], X[M-k] from Z[k] (own registers) and Z[M-k] (one warp shuffle from the mirror lane) -> |X| row
 // The index maps are modelled and checked against numpy.fft.rfft in tools/fft_model.py / tests/test_host_logic.py.
 // Reference semantics: fftwf r2c unnormalised (mfcccpu.cpp:114,189), v = sqrt(re^2+im^2)/N2 (mfcccpu.cpp:203).
 #pragma once
@@ -200,26 +200,36 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneC
         fft8<8>(x);
     }
     __syncwarp();
-    // Z[k] in natural order for the real split, with Z[M] := Z[0] so that the mirror index never wraps
-    if (R == 16) {
+    // Real split without another trip through shared memory: lane lf finalises the bins k = lf + R*m, m = 0..7, and
+    // their mirrors M-k. Z[k] is already in its registers; Z[M-k] lives in lane (R-lf)%R of the same frame:
+    //   R = 16: slot 15-m                          (lane 0 pairs with itself: Z[M-16m] = its own slot 16-m; Z[M] := Z[0])
+    //   R =  8: the other 8-point group, slot 7-m/2 (lane 0: same group; group 0 pairs with slot 8-m/2)
+    // so every lane sends 8 complex values through one shuffle each way.
+    float2 za[8], zb[8];
+    const int src = (threadIdx.x & 31 & ~(R - 1)) | ((R - lf) & (R - 1));
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2++) scratch[lf + 16 * k2] = x[pos16(k2)];
-    } else {
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) {
-            scratch[lf + 16 * k2] = x[pos8(k2)];
-            scratch[lf + 8 + 16 * k2] = x[8 + pos8(k2)];
+    for (int m = 0; m < 8; m++) {
+        float2 own, send, self;
+        if (R == 16) {
+            own = x[pos16(m)];
+            send = x[pos16(15 - m)];
+            self = m == 0 ? x[pos16(0)] : x[pos16(16 - m)];
+        } else {
+            own = (m & 1) ? x[8 + pos8(m >> 1)] : x[pos8(m >> 1)];
+            send = (m & 1) ? x[pos8(7 - (m >> 1))] : x[8 + pos8(7 - (m >> 1))];
+            self = (m & 1) ? x[8 + pos8(7 - (m >> 1))] : (m == 0 ? x[pos8(0)] : x[pos8(8 - (m >> 1))]);
         }
+        float2 got;
+        got.x = __shfl_sync(0xffffffffu, send.x, src);
+        got.y = __shfl_sync(0xffffffffu, send.y, src);
+        za[m] = own;
+        zb[m] = lf == 0 ? self : got;
     }
-    if (lf == 0) scratch[M] = x[0];
-    __syncwarp();
     const float scale = 0.5f / (float)N2; // |2X| * 0.5/N2 == |X|/N2 exactly (powers of two)
-    const float2 *fwd = scratch + lf, *rev = scratch + (M - lf);
     float *mf = mag_out + lf, *mr = mag_out + (M - lf);
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        const float2 a = fwd[R * m];
-        const float2 b = rev[-R * m];
+        const float2 a = za[m], b = zb[m];
         const float2 w = lc.twp[m];
         const float sr = a.x + b.x, si = a.y - b.y; // a + conj(b)
         const float dr = a.x - b.x, di = a.y + b.y; // a - conj(b)
@@ -231,7 +241,7 @@ __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneC
         mr[-R * m] = SCALED ? v2 * scale : v2;
     }
     if (lf == 0) {
-        const float2 a = scratch[M / 2]; // X[M/2] = conj(Z[M/2])
+        const float2 a = R == 16 ? x[pos16(8)] : x[pos8(4)]; // X[M/2] = conj(Z[M/2]): k1 = 0, k2 = M/32
         const float vm = mag_sqrt<FAST>(a.x * a.x + a.y * a.y);
         mag_out[M / 2] = SCALED ? vm * (1.0f / (float)N2) : vm + vm;
     }
