@@ -218,7 +218,7 @@ struct afe_batch {
     int *d_scratch_begin = nullptr;
     float *d_mean = nullptr, *d_scale = nullptr;
     int tc_max = 0, nout_max = 0;
-    int warps = 8;            // warps per CTA of the fused kernel (AFE_FUSED_WARPS=4|8)
+    const int warps = 8;      // warps per CTA of the fused kernel
     int max_tiles_per_utt = 0;
     // In-kernel normalisation lets ONE tile normalise its whole utterance: right for short utterances, a serial
     // bottleneck for a long stream (config 5: 720 tiles) -> those batches take the K2 + K3 kernels.
@@ -294,7 +294,7 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     }
 }
 
-template <int N2, int NZ, int WARPS>
+template <int N2, int NZ, int WARPS, int KF>
 static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm)
 {
     const Derived &d = b->d;
@@ -320,7 +320,7 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS> : k_fused_mfcc<N2, NZ, false, WARPS>;
+    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, KF> : k_fused_mfcc<N2, NZ, false, WARPS, KF>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
     kern<<<t1 - t0, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
     AFE_CUDA(cudaGetLastError());
@@ -338,16 +338,21 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
     const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
     const int R = b->d.M / 16;
     const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    const int key = (b->d.N2 == 512 ? 0 : 4) + (pruned ? 0 : 2) + (b->warps == 8 ? 1 : 0);
+    const int kf = (b->d.nb + 7) / 8; // filters per warp (8 warps): instantiated for 3, 5 and 8
+    const int key = (b->d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
     switch (key) {
-    case 0: launch_fused<512, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 1: launch_fused<512, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 2: launch_fused<512, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 3: launch_fused<512, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 4: launch_fused<256, 13, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 5: launch_fused<256, 13, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 6: launch_fused<256, 16, 4>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    default: launch_fused<256, 16, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 0: launch_fused<512, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 1: launch_fused<512, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 2: launch_fused<512, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 3: launch_fused<512, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 4: launch_fused<512, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 5: launch_fused<512, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 6: launch_fused<256, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 7: launch_fused<256, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 8: launch_fused<256, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 9: launch_fused<256, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    case 10: launch_fused<256, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    default: launch_fused<256, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
     }
 }
 
@@ -464,8 +469,6 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         DeviceGuard g(b->device);
         b->free_plan();
         // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
-        const char *env_w = getenv("AFE_FUSED_WARPS");
-        if (env_w) b->warps = atoi(env_w) == 4 ? 4 : 8;
         // tile geometry: the cepstra tile holds up to 512 frames (<= 6.9 K floats of shared memory)
         const char *env_tc = getenv("AFE_TILE_FRAMES");
         int tc = env_tc ? atoi(env_tc) : 512;

@@ -200,7 +200,9 @@ __device__ __forceinline__ void write_rows(float *__restrict__ orow, const float
 
 } // namespace dev
 
-template <int N2, int NZ, bool FAST, int kFusedWarps>
+// KF = filters per warp in phase 2 (ceil(num_banks / WARPS), rounded up to 3, 5 or 8): the phase is unrolled KF times,
+// so a tight bound keeps the round loop inside the instruction cache.
+template <int N2, int NZ, bool FAST, int kFusedWarps, int KF>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
@@ -289,7 +291,6 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         //      Three unrolled passes over the warp's <= KF filters - sums, logs, DCT - so that the independent filters'
         //      long dependency chains (accumulation, logf) interleave instead of running back to back.
         if (lane < nfr && !(a.debug_skip & 2)) {
-            constexpr int KF = (kMaxBanks + kFusedWarps - 1) / kFusedWarps;
             const float4 *mrow = reinterpret_cast<const float4 *>(s_mags + mag_row(lane) * kMagStride);
             float es[KF];
 #pragma unroll
