@@ -296,8 +296,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
 #pragma unroll
             for (int k = 0; k < KF; k++) {
                 const int b = warp + k * kFusedWarps;
-                float acc = 0.f, acc1 = 0.f; // two chains (bins 0-3 / 4-7 of every chunk), ascending bins within each
-                if (b < a.nb) {              // warp uniform
+                float2 acc = make_float2(0.f, 0.f); // two chains (even / odd bins) in one register pair: FFMA2, ascending bins
+                if (b < a.nb) {                      // warp uniform
                     const int n8 = mc.n8[b];
                     const float4 *wv = mc.wl4 + mc.woff4[b];
                     const float4 *mv = mrow + mc.fchunk[b];
@@ -305,32 +305,31 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                     for (int i = 0; i < n8; i++) {
                         const float4 w0 = wv[2 * i], w1 = wv[2 * i + 1];
                         const float4 m0 = mv[2 * i], m1 = mv[2 * i + 1];
-                        acc = fmaf(w0.x, m0.x, acc); acc1 = fmaf(w1.x, m1.x, acc1);
-                        acc = fmaf(w0.y, m0.y, acc); acc1 = fmaf(w1.y, m1.y, acc1);
-                        acc = fmaf(w0.z, m0.z, acc); acc1 = fmaf(w1.z, m1.z, acc1);
-                        acc = fmaf(w0.w, m0.w, acc); acc1 = fmaf(w1.w, m1.w, acc1);
+                        acc = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc);
+                        acc = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc);
+                        acc = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc);
+                        acc = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc);
                     }
                 }
-                es[k] = acc + acc1;
+                es[k] = acc.x + acc.y;
             }
 #pragma unroll
             for (int k = 0; k < KF; k++)
                 if (warp + k * kFusedWarps < a.nb) es[k] = dev::mel_log<FAST>(es[k]);
             if (a.dct_len > 0) {
-                float cep[16];
+                float2 cep[8];
 #pragma unroll
-                for (int c = 0; c < 16; c++) cep[c] = 0.f;
+                for (int c = 0; c < 8; c++) cep[c] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < KF; k++) {
                     const int b = warp + k * kFusedWarps;
                     if (b < a.nb) {
+                        const float2 e2 = make_float2(es[k], es[k]);
 #pragma unroll
                         for (int c4 = 0; c4 < 4; c4++) {
                             const float4 d4 = mc.dct4[b][c4];
-                            cep[4 * c4 + 0] = fmaf(es[k], d4.x, cep[4 * c4 + 0]);
-                            cep[4 * c4 + 1] = fmaf(es[k], d4.y, cep[4 * c4 + 1]);
-                            cep[4 * c4 + 2] = fmaf(es[k], d4.z, cep[4 * c4 + 2]);
-                            cep[4 * c4 + 3] = fmaf(es[k], d4.w, cep[4 * c4 + 3]);
+                            cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
+                            cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
                         }
                     }
                 }
@@ -338,7 +337,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++)
                     reinterpret_cast<float4 *>(smem + L.off_part + c4 * L.w_scratch)[warp * kRoundFrames + lane] =
-                        make_float4(cep[4 * c4], cep[4 * c4 + 1], cep[4 * c4 + 2], cep[4 * c4 + 3]);
+                        make_float4(cep[2 * c4].x, cep[2 * c4].y, cep[2 * c4 + 1].x, cep[2 * c4 + 1].y);
             } else {
 #pragma unroll
                 for (int k = 0; k < KF; k++)
