@@ -278,14 +278,17 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     memset(&mc, 0, sizeof mc);
     int off4 = 0;
     const float scale = 0.5f / (float)d.N2; // the kernel stores |2X|; scaling by a power of two commutes with rounding
-    for (int b = 0; b < d.nb; b++) {
-        const int j0 = edges[b], j1 = edges[b + 2], s4 = j0 & ~3, n8 = std::max(1, (j1 - s4 + 7) / 8);
-        if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
-        if (s4 + 8 * n8 > kMagStride + 16) throw Error("mel filter too wide for the fused kernel");
-        mc.fchunk[b] = (short)(s4 / 4); mc.n8[b] = (short)n8; mc.woff4[b] = (short)off4;
-        float *w = reinterpret_cast<float *>(mc.wl4 + off4);
-        for (int j = j0; j < j1; j++) w[j - s4] = filters[(size_t)(b % 2) * d.N2 + j] * scale;
-        off4 += 2 * n8;
+    for (int w = 0; w < 8; w++) {           // warp class w owns the filters w, w + 8, ...: their lists are contiguous
+        mc.wstart[w] = (short)off4;
+        for (int b = w; b < d.nb; b += 8) {
+            const int j0 = edges[b], j1 = edges[b + 2], s4 = j0 & ~3, n8 = std::max(1, (j1 - s4 + 7) / 8);
+            if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
+            if (s4 + 8 * n8 > kMagStride + 16) throw Error("mel filter too wide for the fused kernel");
+            mc.desc[b] = (s4 / 4) | (n8 << 16);
+            float *wt = reinterpret_cast<float *>(mc.wl4 + off4);
+            for (int j = j0; j < j1; j++) wt[j - s4] = filters[(size_t)(b % 2) * d.N2 + j] * scale;
+            off4 += 2 * n8;
+        }
     }
     if (d.C > 0) {
         build_dct(d, dct);

@@ -50,12 +50,13 @@ __host__ __device__ constexpr int mag_row(int f) { return 8 * (f >> 3) + ((f >> 
 // Mel / DCT tables passed BY VALUE as a kernel parameter (constant bank): indexed with warp-uniform indices only,
 // read with 128-bit constant loads. Weight lists are zero padded to a multiple of 4 bins; DCT rows to 16 columns.
 struct MelConst {
-    float4 wl4[kMaxWl4];         // filter b = wl4[woff4[b] .. woff4[b] + 2*n8[b]), bins 4*fchunk[b] + 8*i + {0..7}; the weights
+    float4 wl4[kMaxWl4];         // weights of filter b: 2*n8[b] float4 = bins 4*fchunk[b] + 8*i + {0..7}, i < n8[b]. The lists
+                                 // of the filters of one warp class (b = w, w + 8, w + 16, ...) are CONTIGUOUS from
+                                 // wstart[w], in that order, so phase 2 walks them with one running offset. The weights
                                  // carry the 0.5/N2 magnitude scale (an exact power of two), see fft_frame_mag
     float4 dct4[kMaxBanks][4];   // [nb][16]
-    short fchunk[kMaxBanks];     // first 4-bin chunk of filter b (= edges[b] / 4; leading weights are zero)
-    short n8[kMaxBanks];         // 8-bin chunks of filter b
-    short woff4[kMaxBanks];
+    int desc[kMaxBanks];         // fchunk[b] (first 4-bin chunk = edges[b] / 4; leading weights are zero) | n8[b] << 16
+    short wstart[8];             // first float4 of warp class w (8 warps per CTA)
 };
 
 struct FusedArgs {
@@ -157,6 +158,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// keeps a value in its register: the compiler cannot rematerialise the expression it came from
+__device__ __forceinline__ uint32_t opaque(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 } // namespace dev
@@ -251,6 +265,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     for (int i = tid; i < kRoundFrames * kMagStride + 16; i += kFusedThreads) s_mags[i] = 0.f;
     __syncthreads();
 
+    // shared-memory address of this lane's magnitude row in phase 2 (lane = frame of the round), pinned in a register
+    const uint32_t mrow_s = dev::opaque(dev::smem_u32(s_mags) + mag_row(lane) * kMagStride * 4);
     uint32_t parity = 0;
     for (int r = 0; r < nrounds; r++) {
         const int f0 = r * kRoundFrames;            // first frame of the round (tile-local)
@@ -291,27 +307,31 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         //      Three unrolled passes over the warp's <= KF filters - sums, logs, DCT - so that the independent filters'
         //      long dependency chains (accumulation, logf) interleave instead of running back to back.
         if (lane < nfr && !(a.debug_skip & 2)) {
-            const float4 *mrow = reinterpret_cast<const float4 *>(s_mags + mag_row(lane) * kMagStride);
             float es[KF];
+            int woff = mc.wstart[warp]; // running float4 offset into this warp class's weight lists (uniform)
 #pragma unroll
             for (int k = 0; k < KF; k++) {
                 const int b = warp + k * kFusedWarps;
-                float2 acc = make_float2(0.f, 0.f); // two chains (even / odd bins) in one register pair: FFMA2, ascending bins
-                if (b < a.nb) {                      // warp uniform
-                    const int n8 = mc.n8[b];
-                    const float4 *wv = mc.wl4 + mc.woff4[b];
-                    const float4 *mv = mrow + mc.fchunk[b];
-#pragma unroll 2
-                    for (int i = 0; i < n8; i++) {
-                        const float4 w0 = wv[2 * i], w1 = wv[2 * i + 1];
-                        const float4 m0 = mv[2 * i], m1 = mv[2 * i + 1];
-                        acc = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc);
-                        acc = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc);
-                        acc = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc);
-                        acc = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc);
-                    }
+                // four chains (bins 0,1 | 2,3 of every 4-bin group) in two register pairs: FFMA2, ascending bins in each
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+                if (b < a.nb) {              // warp uniform
+                    const int dsc = mc.desc[b];
+                    int n8 = dsc >> 16;      // >= 1
+                    uint32_t maddr = mrow_s + ((dsc & 0xffff) << 4);
+#pragma unroll 1
+                    do {
+                        const float4 w0 = mc.wl4[woff], w1 = mc.wl4[woff + 1];
+                        const float4 m0 = dev::lds128(maddr), m1 = dev::lds128(maddr + 16);
+                        acc0 = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc0);
+                        acc1 = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc1);
+                        acc0 = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc0);
+                        acc1 = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc1);
+                        woff += 2;
+                        maddr += 32;
+                    } while (--n8);
                 }
-                es[k] = acc.x + acc.y;
+                const float2 t = __fadd2_rn(acc0, acc1);
+                es[k] = t.x + t.y;
             }
 #pragma unroll
             for (int k = 0; k < KF; k++)
