@@ -333,9 +333,13 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 const float2 t = __fadd2_rn(acc0, acc1);
                 es[k] = t.x + t.y;
             }
+            // logs two at a time (packed); a filter slot past num_banks holds 0 -> log(1e-30), never used
 #pragma unroll
-            for (int k = 0; k < KF; k++)
-                if (warp + k * kFusedWarps < a.nb) es[k] = dev::mel_log<FAST>(es[k]);
+            for (int k = 0; k + 1 < KF; k += 2) {
+                const float2 e2 = dev::mel_log2<FAST>(make_float2(es[k], es[k + 1]));
+                es[k] = e2.x; es[k + 1] = e2.y;
+            }
+            if (KF & 1) es[KF - 1] = dev::mel_log<FAST>(es[KF - 1]);
             if (a.dct_len > 0) {
                 float2 cep[8];
 #pragma unroll
