@@ -212,6 +212,67 @@ __device__ __forceinline__ void write_rows(float *__restrict__ orow, const float
     }
 }
 
+// Phase 3 for the reference's default regression (l1 = l2 = 3, static + delta + delta-delta): ONE pass, one barrier.
+// A task = (column c, block of R consecutive output rows). The thread loads the R + 12 cepstra of its column that the
+// block depends on (edge frames replicated by clamping, mfcccpu.cpp:243-254), computes the R + 6 extended-axis deltas
+// and the R delta-deltas in registers (same operation order as delta_num), writes the three streams of its rows and
+// keeps the column statistics. 1.5 shared-memory loads per output value instead of 7, no delta rows in shared memory,
+// and the tile's rows leave as 13-float runs that L2 merges into full sectors.
+// s_red3: [rp][width][4] doubles, reduced in group order by the caller (deterministic).
+template <int KIND>
+__device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, const float *__restrict__ s_cep, int c0f, int c1f,
+                                          double *__restrict__ s_red3, int tid, int nthreads, int rs)
+{
+    constexpr int R = 8;
+    const int cols = a.cols, width = a.width, T = tl.T, t0 = tl.t0, nout = tl.nout;
+    const int rp = nthreads / cols, g = tid / cols, c = tid - g * cols;
+    if (g >= rp) return;
+    const int rq = a.q1 ? max(0, T - 6 - t0) : nout; // first row written with the static of 6 rows earlier (Q1)
+    const float rden1 = a.rden1, rden2 = a.rden2;
+    double sum[3] = {0.0, 0.0, 0.0}, sumsq[3] = {0.0, 0.0, 0.0};
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float *obase = a.out + (tl.out_row0 + t0) * (long long)width + c;
+    for (int r0 = g * R; r0 < nout; r0 += rp * R) {
+        float x[R + 12], dh[R + 6];
+#pragma unroll
+        for (int i = 0; i < R + 12; i++) // cepstra of frames t0 + r0 - 6 + i; rows past the tile only feed unused results
+            x[i] = s_cep[(clampi(t0 + r0 - 6 + i, c0f, c1f - 1) - c0f) * cols + c];
+#pragma unroll
+        for (int j = 0; j < R + 6; j++) { // extended-axis delta at frame t0 + r0 - 3 + j (deltacpu.cpp:25)
+            float num = x[j + 4] - x[j + 2];
+            num = fmaf(2.f, x[j + 5] - x[j + 1], num);
+            num = fmaf(3.f, x[j + 6] - x[j], num);
+            dh[j] = num * rden1;
+        }
+        float *orow = obase + (long long)r0 * width;
+#pragma unroll
+        for (int r = 0; r < R; r++, orow += width) {
+            const int row = r0 + r;
+            if (row >= nout) break;
+            float num = dh[r + 4] - dh[r + 2];
+            num = fmaf(2.f, dh[r + 5] - dh[r + 1], num);
+            num = fmaf(3.f, dh[r + 6] - dh[r], num);
+            const float v[3] = {x[r + 6], dh[r + 3], num * rden2};
+            orow[0] = row >= rq ? x[r] : v[0];
+            orow[cols] = v[1];
+            orow[2 * cols] = v[2];
+            if (KIND >= 1 && row < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    sum[k] += (double)v[k];
+                    if (KIND >= 2) sumsq[k] += (double)__fmul_rn(v[k], v[k]);
+                    if (KIND >= 3) { mn[k] = fminf(mn[k], v[k]); mx[k] = fmaxf(mx[k], v[k]); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double *p = s_red3 + ((g * width) + k * cols + c) * 4;
+        p[0] = sum[k]; p[1] = sumsq[k]; p[2] = (double)mn[k]; p[3] = (double)mx[k];
+    }
+}
+
 } // namespace dev
 
 // KF = filters per warp in phase 2 (ceil(num_banks / WARPS), rounded up to 3, 5 or 8): the phase is unrolled KF times,
@@ -398,37 +459,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;
     if (a.debug_skip & 4) return;
-    if (a.nstreams >= 2) {
-        // 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
-        const int rp = kFusedThreads / cols, rl = tid / cols, c = tid - rl * cols;
-        const int nd = nout + 2 * l2;
-        if (rl < rp) {
-            for (int i = rl; i < nd; i += rp) {
-                const int u = t0 - l2 + i;
-                float num;
-                if (u - l1 >= 0 && u + l1 <= T - 1) // interior: no edge replication needed
-                    num = dev::delta_num(s_cep + (u - c0f) * cols + c, cols, l1);
-                else {
-                    num = 0.f;
-                    for (int l = 1; l <= l1; l++) {
-                        const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
-                        const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
-                        num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
-                    }
-                }
-                s_dhat[i * cols + c] = num * a.rden1;
-            }
-        }
-        __syncthreads();
-        if (a.nstreams >= 3) { // 3b: delta-delta of the extended delta rows
-            if (rl < rp)
-                for (int r = rl; r < nout; r += rp)
-                    s_dd[r * cols + c] = dev::delta_num(s_dhat + (r + l2) * cols + c, cols, l2) * a.rden2;
-            __syncthreads();
-        }
-    }
-
-    // 3c: rows out (coalesced: consecutive threads write consecutive floats), column statistics
+    // ownership of the generic row writer and of the fused normalisation: thread = (row group r_off, output column col)
     const int width = a.width;
     const int rpp = kFusedThreads / width; // rows per pass (width <= 128 enforced by the host)
     const bool active = tid < rpp * width;
@@ -439,33 +470,91 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     const float *src = strm == 0 ? s_cep + (t0 - c0f) * cols + c : strm == 1 ? s_dhat + l2 * cols + c : s_dd + c;
     const int rq = (a.q1 && strm == 0) ? max(0, T - D - t0) : nout; // first row written with the shifted static
     const int rs = min(nout, max(0, n_stats - t0));                 // rows [0, rs) enter the statistics
-    double sum = 0.0, sumsq = 0.0;
-    float mn = FLT_MAX, mx = -FLT_MAX;
-    if (active) {
-        float *orow = a.out + (tl.out_row0 + t0) * (long long)width + col;
+    const bool fast3 = a.nstreams == 3 && l1 == 3 && l2 == 3;
+    if (fast3) {
+        // default regression: deltas, rows and statistics in one register-blocked pass (dev::phase3_l3)
+        double *s_red3 = reinterpret_cast<double *>(smem + L.off_mags);
         switch (a.stats_kind) {
-        case 0: dev::write_rows<0>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
-        case 1: dev::write_rows<1>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
-        case 2: dev::write_rows<2>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
-        default: dev::write_rows<3>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+        case 0: dev::phase3_l3<0>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        case 1: dev::phase3_l3<1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        case 2: dev::phase3_l3<2>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        default: dev::phase3_l3<3>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
         }
-    }
-    if (a.partials) {
-        s_red[tid * 4 + 0] = sum;
-        s_red[tid * 4 + 1] = sumsq;
-        s_red[tid * 4 + 2] = (double)mn;
-        s_red[tid * 4 + 3] = (double)mx;
-        __syncthreads();
-        if (tid < width) {
-            double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
-            for (int g = 0; g < rpp; g++) {
-                const double *p = s_red + (g * width + tid) * 4;
-                s0 += p[0]; s1 += p[1];
-                lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+        if (a.partials) {
+            __syncthreads();
+            if (tid < width) {
+                const int rp = kFusedThreads / cols;
+                double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+                for (int g = 0; g < rp; g++) {
+                    const double *p = s_red3 + (g * width + tid) * 4;
+                    s0 += p[0]; s1 += p[1];
+                    lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+                }
+                double *dst = a.partials + ((long long)tile_idx * width + tid) * 4;
+                dst[0] = s0; dst[1] = s1; dst[2] = lo; dst[3] = hi;
             }
-            double *dst = a.partials + ((long long)tile_idx * width + tid) * 4;
-            dst[0] = s0; dst[1] = s1; dst[2] = lo; dst[3] = hi;
         }
+    } else {
+        if (a.nstreams >= 2) {
+            // 3a: delta on the extended axis u in [t0-l2, t0+nout+l2), edge frames replicated (clamped index)
+            const int rp = kFusedThreads / cols, rl = tid / cols, c = tid - rl * cols;
+            const int nd = nout + 2 * l2;
+            if (rl < rp) {
+                for (int i = rl; i < nd; i += rp) {
+                    const int u = t0 - l2 + i;
+                    float num;
+                    if (u - l1 >= 0 && u + l1 <= T - 1) // interior: no edge replication needed
+                        num = dev::delta_num(s_cep + (u - c0f) * cols + c, cols, l1);
+                    else {
+                        num = 0.f;
+                        for (int l = 1; l <= l1; l++) {
+                            const float hi = s_cep[(dev::clampi(u + l, 0, T - 1) - c0f) * cols + c];
+                            const float lo = s_cep[(dev::clampi(u - l, 0, T - 1) - c0f) * cols + c];
+                            num = fmaf((float)l, hi - lo, num); // deltacpu.cpp:25
+                        }
+                    }
+                    s_dhat[i * cols + c] = num * a.rden1;
+                }
+            }
+            __syncthreads();
+            if (a.nstreams >= 3) { // 3b: delta-delta of the extended delta rows
+                if (rl < rp)
+                    for (int r = rl; r < nout; r += rp)
+                        s_dd[r * cols + c] = dev::delta_num(s_dhat + (r + l2) * cols + c, cols, l2) * a.rden2;
+                __syncthreads();
+            }
+        }
+
+        // 3c: rows out (coalesced: consecutive threads write consecutive floats), column statistics
+        double sum = 0.0, sumsq = 0.0;
+        float mn = FLT_MAX, mx = -FLT_MAX;
+        if (active) {
+            float *orow = a.out + (tl.out_row0 + t0) * (long long)width + col;
+            switch (a.stats_kind) {
+            case 0: dev::write_rows<0>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+            case 1: dev::write_rows<1>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+            case 2: dev::write_rows<2>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+            default: dev::write_rows<3>(orow, src, r_off, rpp, nout, rq, rs, cols, width, D, sum, sumsq, mn, mx); break;
+            }
+        }
+        if (a.partials) {
+            s_red[tid * 4 + 0] = sum;
+            s_red[tid * 4 + 1] = sumsq;
+            s_red[tid * 4 + 2] = (double)mn;
+            s_red[tid * 4 + 3] = (double)mx;
+            __syncthreads();
+            if (tid < width) {
+                double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+                for (int g = 0; g < rpp; g++) {
+                    const double *p = s_red + (g * width + tid) * 4;
+                    s0 += p[0]; s1 += p[1];
+                    lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+                }
+                double *dst = a.partials + ((long long)tile_idx * width + tid) * 4;
+                dst[0] = s0; dst[1] = s1; dst[2] = lo; dst[3] = hi;
+            }
+        }
+
     }
 
     // ---- fused normalisation (per-utterance statistics scopes): the LAST tile of an utterance to finish reduces the
