@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafe_cuda.so")
+# AFE_LIB_OVERRIDE: A/B timing of two builds of the same ABI on one box (tools/gpu_ab.sh); never set in production
+LIB_PATH = os.environ.get("AFE_LIB_OVERRIDE") or os.path.join(_HERE, "libafe_cuda.so")
 
 NORM_NONE, NORM_CMN, NORM_CVN, NORM_MINMAX = 0, 1, 2, 3
 DYN_NONE, DYN_DELTA, DYN_ACC = 0, 1, 2

@@ -323,7 +323,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     dev::load_lane_consts<N2, NZ>(lc, a.window2, a.tw_a, a.tw_p, lf);
     // phase 2 reads whole 8-bin chunks: up to 11 floats past a filter's end, i.e. into the next row (or the pad) with a
     // ZERO weight. Rows of frames that are never computed (short tiles) must therefore hold finite numbers.
-    for (int i = tid; i < kRoundFrames * kMagStride + 16; i += kFusedThreads) s_mags[i] = 0.f;
+    for (int i = tid; i < (kRoundFrames * kMagStride + 16) / 4; i += kFusedThreads)
+        reinterpret_cast<float4 *>(s_mags)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     // shared-memory address of this lane's magnitude row in phase 2 (lane = frame of the round), pinned in a register
@@ -370,26 +371,38 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         if (lane < nfr && !(a.debug_skip & 2)) {
             float es[KF];
             int woff = mc.wstart[warp]; // running float4 offset into this warp class's weight lists (uniform)
+            // the first 8-bin chunk of every filter of this warp is loaded up front (2*KF independent 128-bit loads in
+            // flight): 40 of the 89 chunks of the 40-filter bank, so most filters never wait for shared memory
+            int dsc[KF];
+            float4 mf0[KF], mf1[KF];
 #pragma unroll
             for (int k = 0; k < KF; k++) {
                 const int b = warp + k * kFusedWarps;
+                dsc[k] = b < a.nb ? mc.desc[b] : 0;
+                const uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
+                mf0[k] = dev::lds128(maddr);
+                mf1[k] = dev::lds128(maddr + 16);
+            }
+#pragma unroll
+            for (int k = 0; k < KF; k++) {
                 // four chains (bins 0,1 | 2,3 of every 4-bin group) in two register pairs: FFMA2, ascending bins in each
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
-                if (b < a.nb) {              // warp uniform
-                    const int dsc = mc.desc[b];
-                    int n8 = dsc >> 16;      // >= 1
-                    uint32_t maddr = mrow_s + ((dsc & 0xffff) << 4);
-#pragma unroll 1
-                    do {
+                int n8 = dsc[k] >> 16;       // 0 for a slot past num_banks (warp uniform), else >= 1
+                if (n8 > 0) {
+                    uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
+                    float4 m0 = mf0[k], m1 = mf1[k];
+                    for (;;) {
                         const float4 w0 = mc.wl4[woff], w1 = mc.wl4[woff + 1];
-                        const float4 m0 = dev::lds128(maddr), m1 = dev::lds128(maddr + 16);
                         acc0 = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc0);
                         acc1 = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc1);
                         acc0 = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc0);
                         acc1 = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc1);
                         woff += 2;
+                        if (--n8 == 0) break;
                         maddr += 32;
-                    } while (--n8);
+                        m0 = dev::lds128(maddr);
+                        m1 = dev::lds128(maddr + 16);
+                    }
                 }
                 const float2 t = __fadd2_rn(acc0, acc1);
                 es[k] = t.x + t.y;
@@ -433,6 +446,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         if (a.dct_len > 0 && warp < 4) {
             // warp w (< 4) sums columns 4w..4w+3 of every frame over the filter classes, in a fixed order. The partials
             // sit in ITS OWN exchange tile, so no CTA barrier is needed before the next round's FFTs reuse that memory.
+            // (Spreading this sum over all 8 warps was measured 6 % SLOWER, tools/gpu_ab.sh: warps 4-7 running ahead
+            // into the next round's FFTs is what keeps FMA-bound FFT work and LSU-bound mel work mixed on the SM.)
             if (lane < nfr) {
                 const float4 *part = reinterpret_cast<const float4 *>(w_scratch);
                 float4 t = part[lane];
