@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AFE_LIB_OVERRIDE") or os.path.join(_HERE, "libafe_cud
 NORM_NONE, NORM_CMN, NORM_CVN, NORM_MINMAX = 0, 1, 2, 3
 DYN_NONE, DYN_DELTA, DYN_ACC = 0, 1, 2
 STATS_REFERENCE_BLOCK, STATS_UTTERANCE, STATS_CORPUS = 0, 1, 2
-BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM = 1, 2, 4, 8
+BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM, BATCH_WS_KERNEL = 1, 2, 4, 8, 16
 OPT_FIX_FLUSH_STATICS = 1
 
 # every symbol include/afe_cuda.h declares (tests/test_abi.py checks the header against this list and the .so)
@@ -33,7 +33,7 @@ afe_delta_create afe_delta_destroy afe_delta_apply afe_delta_output
 afe_normalizer_create afe_normalizer_destroy afe_normalizer_normalize
 afe_device_malloc afe_device_free afe_memcpy_h2d afe_memcpy_d2h
 afe_batch_create afe_batch_destroy afe_batch_set_window afe_batch_set_alpha afe_batch_set_options afe_batch_set_stream
-afe_batch_plan afe_batch_frame_offsets afe_batch_num_tiles afe_batch_kernel_launches afe_batch_run_device
+afe_batch_plan afe_batch_frame_offsets afe_batch_num_tiles afe_batch_kernel_launches afe_batch_kernel_name afe_batch_run_device
 afe_batch_extract_device afe_batch_corpus_stats afe_normalizer_allreduce afe_batch_set_corpus_stats
 afe_batch_normalize_device afe_batch_synchronize afe_batch_run_host
 afe_cmvn_finalize_host afe_shard_utterances afe_nccl_get_unique_id afe_nccl_comm_init afe_nccl_comm_destroy
@@ -125,6 +125,7 @@ def lib():
             "afe_batch_frame_offsets": (C.c_int, [vp, i64p]),
             "afe_batch_num_tiles": (C.c_int, [vp]),
             "afe_batch_kernel_launches": (C.c_int, [vp]),
+            "afe_batch_kernel_name": (C.c_char_p, [vp]),
             "afe_batch_run_device": (C.c_int, [vp, vp, vp]),
             "afe_batch_extract_device": (C.c_int, [vp, vp, vp]),
             "afe_batch_corpus_stats": (C.c_int, [vp, C.POINTER(vp), ip]),
@@ -463,6 +464,10 @@ class BatchMfcc:
     @property
     def kernel_launches(self):
         return lib().afe_batch_kernel_launches(self._h)
+
+    @property
+    def kernel_name(self):
+        return lib().afe_batch_kernel_name(self._h).decode()
 
     def run_device(self, d_pcm_ptr, d_out_ptr):
         _check(lib().afe_batch_run_device(self._h, C.c_void_p(d_pcm_ptr), C.c_void_p(d_out_ptr)))

@@ -9,6 +9,7 @@
 
 #include "afe_internal.h"
 #include "afe_fused.cuh"
+#include "afe_fused_ws.cuh"
 #include "afe_nccl.h"
 
 namespace afe {
@@ -224,6 +225,13 @@ struct afe_batch {
     // bottleneck for a long stream (config 5: 720 tiles) -> those batches take the K2 + K3 kernels.
     bool fuse_norm() const { return !(flags & AFE_BATCH_UNFUSED_NORM) && max_tiles_per_utt <= 8; }
     FusedSmem L{};
+    WsSmem Lws{};             // layout of the warp-specialised kernel (k_fused_ws)
+    int sm_count = 0;
+    // k_fused_ws (AFE_BATCH_WS_KERNEL, opt-in) covers the reference's default regression (static + delta + delta-delta,
+    // l1 = l2 = 3); everything else takes k_fused_mfcc. Decided at plan time: the two kernels tile differently.
+    bool ws_eligible() const { return (flags & AFE_BATCH_WS_KERNEL) && d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3; }
+    bool ws_planned = false;
+    bool use_ws() const { return ws_planned; }
     MelConst mc;
     float mc_alpha = -1.f;
     int last_launches = 0;
@@ -297,8 +305,7 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     }
 }
 
-template <int N2, int NZ, int WARPS, int KF>
-static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm)
+static FusedArgs make_fused_args(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, bool fuse_norm)
 {
     const Derived &d = b->d;
     FusedArgs a{};
@@ -322,6 +329,28 @@ static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool 
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
+    return a;
+}
+
+template <int N2, int NZ, int KF>
+static void launch_fused_ws(afe_batch *b, const FusedArgs &a, int t0, int t1)
+{
+    const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
+    auto kern = fast ? k_fused_ws<N2, NZ, true, KF> : k_fused_ws<N2, NZ, false, KF>;
+    AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->Lws.total));
+    const int ntiles = t1 - t0;
+    const int grid = std::min(ntiles, b->sm_count); // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
+    kern<<<grid, kWsThreads, b->Lws.total, b->stream>>>(a, b->Lws, b->mc, ntiles);
+    AFE_CUDA(cudaGetLastError());
+    count_launch();
+    b->last_launches++;
+}
+
+template <int N2, int NZ, int WARPS, int KF>
+static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm)
+{
+    const FusedArgs a = make_fused_args(b, d_pcm, d_out, want_stats, t0, fuse_norm);
+    if (b->use_ws()) { launch_fused_ws<N2, NZ, KF>(b, a, t0, t1); return; }
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
     auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, KF> : k_fused_mfcc<N2, NZ, false, WARPS, KF>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
@@ -471,12 +500,34 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         if (n_utts < 1) throw Error("plan: no utterances");
         DeviceGuard g(b->device);
         b->free_plan();
-        // tile geometry: cepstra tile capacity bounded by a 16 KB shared-memory budget and 8 sub-batches
-        // tile geometry: the cepstra tile holds up to 512 frames (<= 6.9 K floats of shared memory)
+        // tile geometry. Generic kernel (2 CTAs per SM): the cepstra tile holds up to 512 frames (<= 27 KB of shared memory).
+        // Warp-specialised kernel (1 CTA per SM): the tile takes what is left of the 227 KB, so that a whole utterance
+        // (<= ~600 frames with 3 magnitude buffers, <= ~1250 with 2, at 13 columns) is ONE tile: no halo, and the
+        // utterance is normalised before its rows are written.
         const char *env_tc = getenv("AFE_TILE_FRAMES");
         int tc = env_tc ? atoi(env_tc) : 512;
-        tc = std::min(tc, (6912 / d.cols) / kRoundFrames * kRoundFrames); // cepstra tile <= 27 KB: still 2 CTAs per SM
-        tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
+        b->ws_planned = false;
+        if (b->ws_eligible()) {
+            int t_max = 0;
+            for (int u = 0; u < n_utts; u++)
+                t_max = std::max<int64_t>(t_max, std::min<int64_t>(std::max<int64_t>(0, (len[u] - (d.W - d.S)) / d.S), 1 << 30));
+            auto base = [&](int nbuf) { return d.N2 == 512 ? ws_smem_layout<512>(d.S, d.cols, 0, nbuf).total : ws_smem_layout<256>(d.S, d.cols, 0, nbuf).total; };
+            auto cap = [&](int nbuf) { return (227 * 1024 - base(nbuf)) / (d.cols * 4) / kRoundFrames * kRoundFrames; };
+            const int need = (t_max + kRoundFrames - 1) / kRoundFrames * kRoundFrames;
+            const int min_tc = kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1);
+            int nbuf = need <= cap(3) ? 3 : 2;
+            int tcw = std::min(std::max(need, min_tc), cap(nbuf));
+            if (env_tc) tcw = std::min(tcw, std::max(atoi(env_tc), min_tc));
+            if (tcw >= min_tc) {
+                b->ws_planned = true;
+                tc = tcw;
+                b->Lws = d.N2 == 512 ? ws_smem_layout<512>(d.S, d.cols, tc, nbuf) : ws_smem_layout<256>(d.S, d.cols, tc, nbuf);
+            }
+        }
+        if (!b->ws_planned) {
+            tc = std::min(tc, (6912 / d.cols) / kRoundFrames * kRoundFrames); // cepstra tile <= 27 KB: still 2 CTAs per SM
+            tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
+        }
         b->tc_max = tc; b->nout_max = tc - 2 * d.D;
         b->n_utts = n_utts;
         b->sample_off.assign(off, off + n_utts);
@@ -504,7 +555,9 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             b->frame_off[u + 1] = b->frame_off[u] + T;
             // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
             int ntile = (T + b->nout_max - 1) / b->nout_max, best_cost = 1 << 30;
-            for (int cand = ntile; cand <= ntile + 3; cand++) {
+            const bool whole = b->ws_planned && T <= b->tc_max; // k_fused_ws: a whole utterance in one tile needs no halo
+            if (whole) ntile = 1;
+            for (int cand = ntile; cand <= ntile + 3 && !whole; cand++) {
                 const int no = (T + cand - 1) / cand;
                 int cost = 0;
                 for (int t0 = 0; t0 < T; t0 += no) {
@@ -533,8 +586,13 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->aligned = aligned;
         b->n_tiles = (int)tiles.size();
         b->n_groups = corpus ? 1 : n_utts;
-        b->L = d.N2 == 512 ? layout_for<512>(b) : layout_for<256>(b);
-        if (b->L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
+        if (b->ws_planned) {
+            if (b->Lws.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
+        } else {
+            b->L = d.N2 == 512 ? layout_for<512>(b) : layout_for<256>(b);
+            if (b->L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
+        }
+        AFE_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
         AFE_CUDA(cudaMalloc(&b->d_tiles, sizeof(Tile) * tiles.size()));
         AFE_CUDA(cudaMemcpy(b->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));
         if (d.p.norm != AFE_NORM_NONE) {
@@ -567,6 +625,7 @@ int afe_batch_frame_offsets(const afe_batch *b, int64_t *fo)
 }
 int afe_batch_num_tiles(const afe_batch *b) { return b->n_tiles; }
 int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
+const char *afe_batch_kernel_name(const afe_batch *b) { return b->use_ws() ? "k_fused_ws" : "k_fused_mfcc"; }
 
 int afe_batch_extract_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
 {

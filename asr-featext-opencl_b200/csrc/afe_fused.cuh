@@ -219,9 +219,13 @@ __device__ __forceinline__ void write_rows(float *__restrict__ orow, const float
 // keeps the column statistics. 1.5 shared-memory loads per output value instead of 7, no delta rows in shared memory,
 // and the tile's rows leave as 13-float runs that L2 merges into full sectors.
 // s_red3: [rp][width][4] doubles, reduced in group order by the caller (deterministic).
-template <int KIND>
+// MODE 0: write the raw rows and keep the statistics (the tile's record is reduced by the caller)
+// MODE 1: statistics only  \ a tile that holds a WHOLE utterance (k_fused_ws) takes the statistics first and then writes
+// MODE 2: write (v - mean) * scale, no statistics  / normalised rows directly: no second trip through L2
+// norm3: mean[3] | scale[3] of this thread's three columns (MODE 2 only)
+template <int KIND, int MODE = 0>
 __device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, const float *__restrict__ s_cep, int c0f, int c1f,
-                                          double *__restrict__ s_red3, int tid, int nthreads, int rs)
+                                          double *__restrict__ s_red3, int tid, int nthreads, int rs, const float *norm3 = nullptr)
 {
     constexpr int R = 8;
     const int cols = a.cols, width = a.width, T = tl.T, t0 = tl.t0, nout = tl.nout;
@@ -231,8 +235,14 @@ __device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, co
     const float rden1 = a.rden1, rden2 = a.rden2;
     double sum[3] = {0.0, 0.0, 0.0}, sumsq[3] = {0.0, 0.0, 0.0};
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float nm[3] = {0.f, 0.f, 0.f}, ns[3] = {1.f, 1.f, 1.f};
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { nm[k] = norm3[k]; ns[k] = norm3[3 + k]; }
+    }
+    const bool cmn = a.norm_type == AFE_NORM_CMN;
     float *obase = a.out + (tl.out_row0 + t0) * (long long)width + c;
-    for (int r0 = g * R; r0 < nout; r0 += rp * R) {
+    for (int r0 = g * R; r0 < (MODE == 1 ? rs : nout); r0 += rp * R) {
         float x[R + 12], dh[R + 6];
 #pragma unroll
         for (int i = 0; i < R + 12; i++) // cepstra of frames t0 + r0 - 6 + i; rows past the tile only feed unused results
@@ -242,7 +252,8 @@ __device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, co
             float num = x[j + 4] - x[j + 2];
             num = fmaf(2.f, x[j + 5] - x[j + 1], num);
             num = fmaf(3.f, x[j + 6] - x[j], num);
-            dh[j] = num * rden1;
+            dh[j] = __fmul_rn(num, rden1); // rounded like the stored delta row of the reference: never contracted into the
+                                           // differences below
         }
         float *orow = obase + (long long)r0 * width;
 #pragma unroll
@@ -252,11 +263,18 @@ __device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, co
             float num = dh[r + 4] - dh[r + 2];
             num = fmaf(2.f, dh[r + 5] - dh[r + 1], num);
             num = fmaf(3.f, dh[r + 6] - dh[r], num);
-            const float v[3] = {x[r + 6], dh[r + 3], num * rden2};
-            orow[0] = row >= rq ? x[r] : v[0];
-            orow[cols] = v[1];
-            orow[2 * cols] = v[2];
-            if (KIND >= 1 && row < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
+            const float v[3] = {x[r + 6], dh[r + 3], __fmul_rn(num, rden2)};
+            if (MODE == 0) {
+                orow[0] = row >= rq ? x[r] : v[0];
+                orow[cols] = v[1];
+                orow[2 * cols] = v[2];
+            } else if (MODE == 2) { // same operations as the in-place normaliser: v - m, or (v - m) * scale
+                const float w0 = row >= rq ? x[r] : v[0];
+                orow[0] = cmn ? w0 - nm[0] : (w0 - nm[0]) * ns[0];
+                orow[cols] = cmn ? v[1] - nm[1] : (v[1] - nm[1]) * ns[1];
+                orow[2 * cols] = cmn ? v[2] - nm[2] : (v[2] - nm[2]) * ns[2];
+            }
+            if (MODE != 2 && KIND >= 1 && row < rs) { // normalizercpu.cpp:31-66: double sums of float values / float products
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     sum[k] += (double)v[k];
@@ -266,10 +284,12 @@ __device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, co
             }
         }
     }
+    if (MODE != 2) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        double *p = s_red3 + ((g * width) + k * cols + c) * 4;
-        p[0] = sum[k]; p[1] = sumsq[k]; p[2] = (double)mn[k]; p[3] = (double)mx[k];
+        for (int k = 0; k < 3; k++) {
+            double *p = s_red3 + ((g * width) + k * cols + c) * 4;
+            p[0] = sum[k]; p[1] = sumsq[k]; p[2] = (double)mn[k]; p[3] = (double)mx[k];
+        }
     }
 }
 

@@ -185,7 +185,8 @@ def run_b200(args):
 
     p = params_dict()
     ap = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in p.items() if k != "alpha"})
-    flags = afe.BATCH_Q1_EXACT | (afe.BATCH_FAST_MATH if args.fast_math else 0) | (afe.BATCH_NO_TMA if args.no_tma else 0)
+    flags = (afe.BATCH_Q1_EXACT | (afe.BATCH_FAST_MATH if args.fast_math else 0) | (afe.BATCH_NO_TMA if args.no_tma else 0) |
+             (afe.BATCH_WS_KERNEL if args.ws_kernel else 0))
     # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -313,7 +314,7 @@ def run_b200(args):
         k1 = float(np.mean(k1_ms))
         alg_bytes = frames * (2 * S + 4 * WIDTH)
         achieved = alg_bytes / (k1 * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_fused_mfcc<512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": b.kernel_name + "<512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1, "kernel_share_of_step": k1 / ms_per_step,
                 "note": "fp32-issue bound (FFT butterflies), not HBM bound; see DESIGN.md"}
@@ -344,7 +345,7 @@ def run_b200(args):
                 "dtype": "f32", "data": "synthetic", "config": workload_config(n_utts, world),
                 "audio_hours_per_s": value * S / SR / 3600.0, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks, "corpus_cmvn": corpus,
-                "kernels_per_step": ["k_fused_mfcc"],
+                "kernels_per_step": [b.kernel_name],
                 "tiles_per_gpu": b.num_tiles, "flags": {"fast_math": bool(args.fast_math), "tma": not args.no_tma}}
         print(json.dumps(line), flush=True)
     b.close()
@@ -360,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU (BASELINE config 3: 10000)")
     ap.add_argument("--fast-math", action="store_true")
+    ap.add_argument("--ws-kernel", action="store_true", help="the warp-specialised persistent k_fused_ws instead of k_fused_mfcc (A/B)")
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

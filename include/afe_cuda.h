@@ -151,7 +151,11 @@ enum afe_batch_flags {
     AFE_BATCH_Q1_EXACT = 1,        /* reproduce the single-block flush quirk Q1 (statics of the last D rows) */
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
     AFE_BATCH_FAST_MATH = 4,       /* MUFU log2 approximation in the fused kernel (tolerance-checked in tests) */
-    AFE_BATCH_UNFUSED_NORM = 8     /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
+    AFE_BATCH_UNFUSED_NORM = 8,    /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
+    AFE_BATCH_WS_KERNEL = 16       /* run the warp-specialised persistent kernel k_fused_ws (producer warps FFT, consumer warps
+                                      mel/DCT/deltas; whole utterances per tile) when the regression is the reference's
+                                      default (static + delta + delta-delta, l1 = l2 = 3). Measured 1.6 % slower than
+                                      k_fused_mfcc at BASELINE config 3 (profiles/r01_ws_vs_generic.txt): opt-in. */
 };
 
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out);
@@ -170,6 +174,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *sample_offsets, const int64_t *s
 int afe_batch_frame_offsets(const afe_batch *b, int64_t *frame_offsets);
 int afe_batch_num_tiles(const afe_batch *b);
 int afe_batch_kernel_launches(const afe_batch *b); /* kernels launched by the last run */
+const char *afe_batch_kernel_name(const afe_batch *b); /* fused kernel the current plan runs: "k_fused_ws" | "k_fused_mfcc" */
 /* d_pcm: DEVICE int16 buffer covering every [offset, offset+length) (+16 B slack after the last sample),
  * d_out: DEVICE float[total_frames][width]. Asynchronous on the handle's stream. */
 int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out);

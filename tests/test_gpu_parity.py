@@ -291,6 +291,28 @@ def test_batch_is_deterministic_and_order_independent():
         np.testing.assert_array_equal(a[i], e[i])
 
 
+@pytest.mark.parametrize("norm", ["none", "cmn", "cvn", "minmax"])
+def test_batch_ws_equals_generic_kernel(norm):
+    """The warp-specialised persistent kernel (k_fused_ws, AFE_BATCH_WS_KERNEL, for the reference's regression l1 = l2 = 3)
+    and the default kernel (k_fused_mfcc) are two schedules of the same arithmetic, tiled differently
+    (whole utterances vs <= 500-frame tiles with halos): rows are bitwise equal without normalisation; with it the mean /
+    scale may differ by one rounding (statistics records summed in a different order), i.e. <= 2e-6 on the rows.
+    Ragged batch with more tiles than SMs, utterances longer than a tile (tile-by-tile normalisation), with and without
+    TMA staging, Q1, and the 8 kHz / 256-point shape."""
+    for kw, n, length, sr in ((dict(num_banks=40), 200, 160000, 16000.0), (dict(num_banks=23), 12, 330000, 16000.0),
+                              (dict(window_size=200, shift=80, num_banks=20, sample_rate=8000.0, high_freq=4000.0), 40, 90000, 8000.0)):
+        p = ol.default_params(norm=norm, dyn="acc", **kw)
+        utts = synth_utterances(n, length, seed=21, ragged=True, sr=sr)
+        for extra in (0, afe.BATCH_NO_TMA, afe.BATCH_Q1_EXACT):
+            a = run_batch(p, utts, flags=extra | afe.BATCH_WS_KERNEL)
+            b = run_batch(p, utts, flags=extra)
+            for i in range(len(utts)):
+                if norm == "none":
+                    np.testing.assert_array_equal(a[i], b[i])
+                else:
+                    np.testing.assert_allclose(a[i], b[i], rtol=0, atol=2e-6 if norm == "cmn" else 2e-5)
+
+
 def test_batch_linearity_property():
     """Without log the path would be linear; with it, scaling the PCM by 2 shifts every log-mel by ln 2, i.e. adds
     ln2 * sum_k M[k][j] to cepstrum j and leaves deltas unchanged (checked on c0: sqrt(2/nb)*nb*ln 2)."""

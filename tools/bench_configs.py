@@ -27,7 +27,7 @@ def run(name, params, lens, sr, steps=10):
     pcm = torch.zeros(pos + 64, dtype=torch.int16, device=dev)
     for o, n in zip(offs, lens):
         pcm[o:o + n] = synth(n, sr)
-    b = afe.BatchMfcc(params, 0, flags=afe.BATCH_Q1_EXACT)
+    b = afe.BatchMfcc(params, 0, flags=afe.BATCH_Q1_EXACT | (afe.BATCH_WS_KERNEL if os.environ.get("AFE_WS") else 0))
     b.set_stream(stream.cuda_stream)
     frames = b.plan(np.array(offs, np.int64), np.array(lens, np.int64))
     out = torch.empty((frames, b.width), dtype=torch.float32, device=dev)
@@ -43,7 +43,7 @@ def run(name, params, lens, sr, steps=10):
     bytes_alg = frames * (2 * S + 4 * b.width)
     print(json.dumps({"case": name, "frames": frames, "utterances": len(lens), "tiles": b.num_tiles, "ms": ms,
                       "frames_per_s": frames / ms * 1e3, "audio_hours_per_s": frames * S / sr / 3600 / ms * 1e3,
-                      "achieved_GBps": bytes_alg / ms / 1e6, "finite": bool(torch.isfinite(out).all())}), flush=True)
+                      "achieved_GBps": bytes_alg / ms / 1e6, "kernel": b.kernel_name, "finite": bool(torch.isfinite(out).all())}), flush=True)
     b.close()
 
 rng = np.random.default_rng(1)
