@@ -1,24 +1,27 @@
 // K1: the fused hot-path kernel.  int16 PCM -> window -> real FFT -> |X|/N2 -> mel+log -> DCT -> delta/delta-delta
-// -> feature rows (+ per-tile column statistics): one HBM read of PCM and one HBM write of features per frame.
+// -> feature rows (+ per-tile column statistics, + per-utterance normalisation): one HBM read of PCM and one HBM write
+// of features per frame.
 //
-// Work item = (utterance, tile of `nout` output frames). A CTA (4 warps) computes the cepstra of its tile plus a halo
-// of D = l1+l2 frames on each side (clamped at the utterance edges, where the reference replicates the edge frame,
-// mfcccpu.cpp:243-254) in rounds of 32 frames:
-//   stage 0  each warp stages the PCM of ITS 8 frames with one cp.async.bulk (TMA, SASS UBLKCP) into its own buffer,
+// Work item = (utterance, tile of `nout` output frames). A CTA (8 warps, 2 CTAs per SM) computes the cepstra of its tile
+// plus a halo of D = l1+l2 frames on each side (clamped at the utterance edges, where the reference replicates the edge
+// frame, mfcccpu.cpp:243-254) in rounds of 32 frames:
+//   stage 0  each warp stages the PCM of ITS 4 frames with one cp.async.bulk (TMA, SASS UBLKCP) into its own buffer,
 //            completion on its own mbarrier; the next round's copy is issued as soon as this round's FFTs are done
-//   phase 1  each warp: 32/(WARPS*FPW) calls of the in-register FFT + magnitude (afe_fft.cuh) -> mags[32][260] (CTA
+//   phase 1  each warp: 4/FPW calls of the in-register FFT + magnitude (afe_fft.cuh, packed FP32) -> mags[32][260] (CTA
 //            shared). Frame f lives in row mag_row(f): the two adjacent frames of one call land 4 rows = 16 banks
 //            apart, and the 8 frames of a quarter warp occupy 8 consecutive rows, so phase 2's "lane = frame" 128-bit
 //            reads (row stride 65 chunks = 1 mod 8) are conflict free
-//   phase 2  mel + log + DCT, ONE THREAD PER FRAME, warp w owning the filters b = w (mod 4). The triangular weights and
-//            the DCT matrix are kernel parameters, i.e. constant-bank operands: they cost no shared-memory bandwidth,
-//            which is what bounds this kernel (v3/v4 re-loaded weights per lane: 116 of 245 smem wavefronts per frame,
-//            profiles/r01_v3_k_fused_summary.txt). Accumulation per filter runs in the reference's ascending-bin order
-//            (mfcccpu.cpp:192-220). Per-warp partial cepstra are summed in a fixed order -> cep[tile][cols].
-//   phase 3  delta on the extended axis -> smem, then rows [static | delta | delta-delta] are written coalesced;
-//            column sums / sums of squares (double) / min / max of the tile go to a per-tile partial record.
-// Two CTA barriers per 32 frames; both phases keep all four warps equally busy (v1 serialised phase 2 on one warp and
-// lost 39 % of its issue slots at the barrier, profiles/r01_v1_k_fused_summary.txt).
+//   phase 2  mel + log + DCT, ONE THREAD PER FRAME, warp w owning the filters b = w (mod 8). The triangular weights and
+//            the DCT matrix are kernel parameters, i.e. constant-bank operands (LDCU.64 -> uniform-register operand of
+//            FFMA2): they cost no shared-memory bandwidth (v3/v4 re-loaded weights per lane: 116 of 245 smem wavefronts
+//            per frame, profiles/r01_v3_k_fused_summary.txt). Accumulation per filter runs in ascending-bin order
+//            (mfcccpu.cpp:192-220) in four chains. Per-warp partial cepstra are summed in a fixed order -> cep[tile][cols].
+//   phase 3  default regression (l1 = l2 = 3): one register-blocked pass computes delta / delta-delta, writes the rows and
+//            keeps column sums / sums of squares (double) / min / max -> per-tile record (dev::phase3_l3). Otherwise:
+//            delta rows through shared memory, then coalesced row writes.
+//   norm     the last tile of an utterance to finish reduces the records and normalises the utterance in place (L2).
+// Two CTA barriers per 32 frames (v1 serialised phase 2 on one warp and lost 39 % of its issue slots at the barrier,
+// profiles/r01_v1_k_fused_summary.txt). The warp-specialised alternative is afe_fused_ws.cuh.
 // Replaces, for whole utterances: segmenter.cl, AppleFFT fft0, mfcc.cl kernelTranspose+kernelFilter, DCT.cl,
 // delta.cl and norm.cl:kernelSum.
 #pragma once

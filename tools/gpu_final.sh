@@ -11,6 +11,6 @@ if [ $rc -eq 0 ]; then
   timeout 600 $cmd > gpurun_out/plain_small.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_|nccl|Kernel" -c 60 --csv --log-file gpurun_out/launches.csv $cmd > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused_mfcc -s 3 -c 1 -o gpurun_out/prof_final $cmd > gpurun_out/ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused_ -s 3 -c 1 -o gpurun_out/prof_final $cmd > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
