@@ -69,3 +69,47 @@ def test_driver_reports_reference_error_strings(tmp_path):
     write_wav(wav, np.zeros(400 + 160 * 5, np.int16))
     r = subprocess.run([EXE, "--dyn", "2", wav, str(tmp_path / "o.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "window count is too small" in r.stderr
+
+
+def read_htk(path):
+    raw = open(path, "rb").read()
+    n, period, size, kind = struct.unpack(">iihh", raw[:12])
+    return n, period, size, kind, np.frombuffer(raw[12:], ">f4").reshape(n, size // 4).astype(np.float32)
+
+
+def test_batch_mode_scp_and_htk(oracle, tmp_path):
+    """--batch: all files in ONE fused launch; --scp list; HTK parameter files. Rows must equal the
+    per-file streaming driver within the tolerance and the oracle's single-block result (Q1 reproduced)."""
+    names = ["a1", "a0001", "a3"]
+    pcm = load_pcm()
+    scp = tmp_path / "list.scp"
+    with open(scp, "w") as f:
+        for n in names:
+            write_wav(str(tmp_path / f"{n}.wav"), pcm[n])
+            f.write(f"{tmp_path / (n + '.wav')} {tmp_path / (n + '.htk')}\n")
+    opts = ["--banks", "23", "--ceps", "12", "--c0", "1", "--norm", "1", "--dyn", "2", "--l1", "3", "--l2", "3"]
+    r = run(opts + ["--batch", "1", "--htk", "1", "--scp", str(scp)])
+    assert "1 kernel launch(es)" in r.stderr and f"batch: {len(names)} files" in r.stderr, r.stderr
+    p = ol.default_params(norm="cmn", dyn="acc")
+    for n in names:
+        rows, period, size, kind, got = read_htk(str(tmp_path / f"{n}.htk"))
+        want = oracle.extract(p, [pcm[n]], sample_limit=1 << 22)[0][0]
+        assert (rows, period, size) == (len(want), 100000, 4 * 39)
+        assert kind == (6 | 0x2000 | 0x100 | 0x200 | 0x800)   # MFCC_0_D_A_Z
+        assert_close(got, want, p, n + " batch htk")
+        # streaming driver, same file, text output
+        txt = str(tmp_path / f"{n}.txt")
+        run(opts + [str(tmp_path / f"{n}.wav"), txt])
+        vals = np.array([[float(x) for x in l.strip("| ").split(" | ")] for l in open(txt).read().splitlines()])
+        assert np.abs(vals[:, 1:] - got).max() < 2e-4 + 1e-6
+
+
+def test_batch_mode_text_equals_streaming_layout(tmp_path):
+    pcm = load_pcm()["a1"]
+    wav = str(tmp_path / "a1.wav")
+    write_wav(wav, pcm)
+    run(["--banks", "23", "--norm", "0", "--dyn", "0", "--batch", "1", wav, str(tmp_path / "b.txt")])
+    run(["--banks", "23", "--norm", "0", "--dyn", "0", wav, str(tmp_path / "s.txt")])
+    b, s = open(tmp_path / "b.txt").read().splitlines(), open(tmp_path / "s.txt").read().splitlines()
+    assert len(b) == len(s) == 504
+    assert [l.split(" | ")[0] for l in b] == [l.split(" | ")[0] for l in s]   # timestamps (Q6) byte for byte
