@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AFE_LIB_OVERRIDE") or os.path.join(_HERE, "libafe_cud
 NORM_NONE, NORM_CMN, NORM_CVN, NORM_MINMAX = 0, 1, 2, 3
 DYN_NONE, DYN_DELTA, DYN_ACC = 0, 1, 2
 STATS_REFERENCE_BLOCK, STATS_UTTERANCE, STATS_CORPUS = 0, 1, 2
-BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM, BATCH_WS_KERNEL = 1, 2, 4, 8, 16
+BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM, BATCH_WS_KERNEL, BATCH_NO_CLUSTER = 1, 2, 4, 8, 16, 32
 OPT_FIX_FLUSH_STATICS = 1
 
 # every symbol include/afe_cuda.h declares (tests/test_abi.py checks the header against this list and the .so)

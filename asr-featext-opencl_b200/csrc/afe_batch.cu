@@ -346,20 +346,62 @@ static void launch_fused_ws(afe_batch *b, const FusedArgs &a, int t0, int t1)
     b->last_launches++;
 }
 
+// cluster: 0 = plain launch (ticket scheme or no fused normalisation); 1, 2, ... = clustered launch, one cluster per
+// utterance of `cluster` tiles, normalisation inside the cluster (FusedArgs::cluster_norm)
 template <int N2, int NZ, int WARPS, int KF>
-static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm)
+static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm,
+                         int cluster = 0)
 {
-    const FusedArgs a = make_fused_args(b, d_pcm, d_out, want_stats, t0, fuse_norm);
+    FusedArgs a = make_fused_args(b, d_pcm, d_out, want_stats, t0, fuse_norm);
     if (b->use_ws()) { launch_fused_ws<N2, NZ, KF>(b, a, t0, t1); return; }
     const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
     auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, KF> : k_fused_mfcc<N2, NZ, false, WARPS, KF>;
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    kern<<<t1 - t0, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
+    if (cluster > 0) {
+        a.cluster_norm = 1;
+        a.counters = nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(t1 - t0); cfg.blockDim = dim3(32 * WARPS); cfg.dynamicSmemBytes = b->L.total; cfg.stream = b->stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        AFE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b->L, b->mc));
+    } else
+        kern<<<t1 - t0, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
     AFE_CUDA(cudaGetLastError());
     count_launch();
     b->last_launches++;
 }
 
+static void dispatch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm,
+                           int cluster)
+{
+    const int R = b->d.M / 16;
+    const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
+    const int kf = (b->d.nb + 7) / 8; // filters per warp (8 warps): instantiated for 3, 5 and 8
+    const int key = (b->d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
+    switch (key) {
+    case 0: launch_fused<512, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 1: launch_fused<512, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 2: launch_fused<512, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 3: launch_fused<512, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 4: launch_fused<512, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 5: launch_fused<512, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 6: launch_fused<256, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 7: launch_fused<256, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 8: launch_fused<256, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 9: launch_fused<256, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    case 10: launch_fused<256, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    default: launch_fused<256, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    }
+}
+
+// Tiles [t0, t1) (whole utterances). With fused normalisation and the default regression the utterances are taken in
+// runs of equal tile count and every run of 1- or 2-tile utterances becomes ONE clustered launch (cluster = utterance);
+// a batch that would need more than kMaxClusterRuns launches (ragged lengths in random order) or other tile counts keeps
+// the ticket scheme (last tile normalises through L2) in a single launch.
+constexpr int kMaxClusterRuns = 8;
 static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1, bool fuse_norm = false)
 {
     if (t1 < 0) t1 = b->n_tiles;
@@ -367,25 +409,25 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
     if (!b->window_set) throw Error("set_window must be called before running");
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
     if (b->mc_alpha != b->alpha) { build_mel_const(b->d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
-    const bool want_stats = b->d.p.norm != AFE_NORM_NONE;
-    const int R = b->d.M / 16;
-    const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    const int kf = (b->d.nb + 7) / 8; // filters per warp (8 warps): instantiated for 3, 5 and 8
-    const int key = (b->d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
-    switch (key) {
-    case 0: launch_fused<512, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 1: launch_fused<512, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 2: launch_fused<512, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 3: launch_fused<512, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 4: launch_fused<512, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 5: launch_fused<512, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 6: launch_fused<256, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 7: launch_fused<256, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 8: launch_fused<256, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 9: launch_fused<256, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    case 10: launch_fused<256, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
-    default: launch_fused<256, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm); break;
+    const Derived &d = b->d;
+    const bool want_stats = d.p.norm != AFE_NORM_NONE;
+    const bool cluster_ok = fuse_norm && want_stats && !b->use_ws() && !(b->flags & AFE_BATCH_NO_CLUSTER) &&
+                            d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
+    if (cluster_ok) {
+        struct Run { int t0, t1, cluster; };
+        std::vector<Run> runs;
+        const int u0 = (int)(std::lower_bound(b->h_tile_begin.begin(), b->h_tile_begin.end(), t0) - b->h_tile_begin.begin());
+        for (int u = u0; u < b->n_utts && b->h_tile_begin[u] < t1 && (int)runs.size() <= kMaxClusterRuns; u++) {
+            const int nt = b->h_tile_begin[u + 1] - b->h_tile_begin[u], cl = nt <= 2 ? nt : 0;
+            if (!runs.empty() && runs.back().cluster == cl) runs.back().t1 = b->h_tile_begin[u + 1];
+            else runs.push_back({b->h_tile_begin[u], b->h_tile_begin[u + 1], cl});
+        }
+        if ((int)runs.size() <= kMaxClusterRuns && !runs.empty() && runs.front().t0 == t0 && runs.back().t1 == t1) {
+            for (const Run &r : runs) dispatch_fused(b, d_pcm, d_out, want_stats, r.t0, r.t1, fuse_norm, r.cluster);
+            return;
+        }
     }
+    dispatch_fused(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, 0);
 }
 
 static void run_reduce(afe_batch *b, int g0 = 0, int g1 = -1)

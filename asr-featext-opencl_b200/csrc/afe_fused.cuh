@@ -69,6 +69,8 @@ struct FusedArgs {
     const float2 *window2, *tw_a, *tw_p;
     double *partials;    // [ntiles][width][4] or nullptr (indexed by absolute tile number)
     int *counters;       // [groups] arrival tickets for the fused normalisation (self-resetting), or nullptr
+    int cluster_norm;    // 1: the launch is clustered, one cluster = the tiles of ONE utterance; the tiles exchange their
+                         // statistics records through distributed shared memory and write normalised rows directly
     int tile_base;       // absolute index of this launch's first tile
     int norm_type, norm_after_dyn;
     int debug_skip;      // timing experiments only (AFE_DEBUG_SKIP): 1 skip FFT calls, 2 skip mel/DCT, 4 skip phase 3 + normalise
@@ -171,6 +173,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
 __device__ __forceinline__ uint32_t opaque(uint32_t v)
 {
     asm volatile("" : "+r"(v));
+    return v;
+}
+
+// ---- thread-block clusters: barrier over all CTAs of the cluster, read of a peer CTA's shared memory (DSMEM)
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_size()
+{
+    uint32_t n;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+    return n;
+}
+__device__ __forceinline__ double ld_peer_f64(const double *local, uint32_t rank)
+{
+    uint32_t peer;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(peer) : "memory");
     return v;
 }
 
@@ -509,7 +531,56 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     const int rq = (a.q1 && strm == 0) ? max(0, T - D - t0) : nout; // first row written with the shifted static
     const int rs = min(nout, max(0, n_stats - t0));                 // rows [0, rs) enter the statistics
     const bool fast3 = a.nstreams == 3 && l1 == 3 && l2 == 3;
-    if (fast3) {
+    if (fast3 && a.cluster_norm) {
+        // One cluster = the tiles of one utterance (cluster rank = tile number). Statistics first (MODE 1), records
+        // exchanged through distributed shared memory and summed in tile order - the order of the ticket scheme below and
+        // of K2, so the results are bitwise the same -, then every tile writes its rows already normalised (MODE 2):
+        // the features make ONE trip to HBM and none back through L2.
+        double *s_red3 = reinterpret_cast<double *>(smem + L.off_mags);
+        double *s_rec = reinterpret_cast<double *>(smem + L.off_mags + 25 * 1024);
+        float *s_mean = reinterpret_cast<float *>(smem + L.off_mags + 30 * 1024), *s_scale = s_mean + width;
+        switch (a.stats_kind) {
+        case 1: dev::phase3_l3<1, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        case 2: dev::phase3_l3<2, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        default: dev::phase3_l3<3, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
+        }
+        __syncthreads();
+        if (tid < width) {
+            const int rp = kFusedThreads / cols;
+            double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+            for (int g = 0; g < rp; g++) {
+                const double *p = s_red3 + (g * width + tid) * 4;
+                s0 += p[0]; s1 += p[1];
+                lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
+            }
+            double *rec = s_rec + tid * 4;
+            rec[0] = s0; rec[1] = s1; rec[2] = lo; rec[3] = hi;
+        }
+        dev::cluster_sync(); // every tile's record is in its CTA's shared memory
+        if (tid < width) {   // normalizercpu.cpp:31-66
+            const double *rec = s_rec + (a.norm_after_dyn ? tid : tid % cols) * 4;
+            const uint32_t ncta = dev::cluster_size();
+            double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
+            for (uint32_t t = 0; t < ncta; t++) {
+                s0 += dev::ld_peer_f64(rec, t); s1 += dev::ld_peer_f64(rec + 1, t);
+                lo = fmin(lo, dev::ld_peer_f64(rec + 2, t)); hi = fmax(hi, dev::ld_peer_f64(rec + 3, t));
+            }
+            const double n = (double)n_stats;
+            float m = (float)(s0 / n), sc = 1.f;
+            if (a.norm_type == AFE_NORM_CVN) sc = (float)sqrt((n - 1.0) / (s1 - s0 * (s0 / n)));
+            else if (a.norm_type == AFE_NORM_MINMAX) sc = 1.f / fmaxf(fabsf((float)lo - m), fabsf((float)hi - m));
+            if (!a.norm_after_dyn && tid >= cols) m = 0.f;
+            s_mean[tid] = m; s_scale[tid] = sc;
+        }
+        __syncthreads();
+        {
+            const int cc = tid % cols;
+            const float norm3[6] = {s_mean[cc], s_mean[cols + cc], s_mean[2 * cols + cc],
+                                    s_scale[cc], s_scale[cols + cc], s_scale[2 * cols + cc]};
+            dev::phase3_l3<0, 2>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs, norm3);
+        }
+        dev::cluster_sync(); // no CTA leaves while a peer may still read its record
+    } else if (fast3) {
         // default regression: deltas, rows and statistics in one register-blocked pass (dev::phase3_l3)
         double *s_red3 = reinterpret_cast<double *>(smem + L.off_mags);
         switch (a.stats_kind) {

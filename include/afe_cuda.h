@@ -152,6 +152,8 @@ enum afe_batch_flags {
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
     AFE_BATCH_FAST_MATH = 4,       /* MUFU log2 approximation in the fused kernel (tolerance-checked in tests) */
     AFE_BATCH_UNFUSED_NORM = 8,    /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
+    AFE_BATCH_NO_CLUSTER = 32,     /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
+                                      place via L2) instead of thread-block clusters + distributed shared memory (A-B test) */
     AFE_BATCH_WS_KERNEL = 16       /* run the warp-specialised persistent kernel k_fused_ws (producer warps FFT, consumer warps
                                       mel/DCT/deltas; whole utterances per tile) when the regression is the reference's
                                       default (static + delta + delta-delta, l1 = l2 = 3). Measured 1.6 % slower than

@@ -2,8 +2,8 @@
 # parity tests, then the device-only bench: default kernel and the opt-in warp-specialised kernel, same box
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu --timeout 300 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
-for v in default ws; do
-  extra=""; [ $v = ws ] && extra="--ws-kernel"
+for v in default nocluster ws; do
+  extra=""; [ $v = ws ] && extra="--ws-kernel"; [ $v = nocluster ] && extra="--no-cluster"
   timeout 300 python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu $extra $BENCH_ARGS > gpurun_out/check_$v.log 2>&1
   python - <<PY
 import json
