@@ -398,10 +398,11 @@ static void dispatch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, boo
 }
 
 // Tiles [t0, t1) (whole utterances). With fused normalisation and the default regression the utterances are taken in
-// runs of equal tile count and every run of 1- or 2-tile utterances becomes ONE clustered launch (cluster = utterance);
+// runs of equal tile count and every run of utterances with 1 to kMaxClusterTiles tiles becomes ONE clustered launch (cluster = utterance);
 // a batch that would need more than kMaxClusterRuns launches (ragged lengths in random order) or other tile counts keeps
 // the ticket scheme (last tile normalises through L2) in a single launch.
 constexpr int kMaxClusterRuns = 8;
+constexpr int kMaxClusterTiles = 4; // utterances of up to 4 tiles (~20 s) form a cluster; longer ones keep the ticket scheme
 static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1, bool fuse_norm = false)
 {
     if (t1 < 0) t1 = b->n_tiles;
@@ -418,7 +419,7 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
         std::vector<Run> runs;
         const int u0 = (int)(std::lower_bound(b->h_tile_begin.begin(), b->h_tile_begin.end(), t0) - b->h_tile_begin.begin());
         for (int u = u0; u < b->n_utts && b->h_tile_begin[u] < t1 && (int)runs.size() <= kMaxClusterRuns; u++) {
-            const int nt = b->h_tile_begin[u + 1] - b->h_tile_begin[u], cl = nt <= 2 ? nt : 0;
+            const int nt = b->h_tile_begin[u + 1] - b->h_tile_begin[u], cl = nt <= kMaxClusterTiles ? nt : 0;
             if (!runs.empty() && runs.back().cluster == cl) runs.back().t1 = b->h_tile_begin[u + 1];
             else runs.push_back({b->h_tile_begin[u], b->h_tile_begin[u + 1], cl});
         }

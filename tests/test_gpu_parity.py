@@ -296,12 +296,14 @@ def test_batch_cluster_normalisation_equals_ticket_scheme(norm):
     """Fused normalisation inside a thread-block cluster (one cluster = the 1 or 2 tiles of an utterance, statistics
     records exchanged through distributed shared memory, rows written already normalised) against the ticket scheme
     (AFE_BATCH_NO_CLUSTER: last tile normalises in place through L2) and against K2 + K3: bitwise equal. Batches of
-    2-tile utterances, of 1-tile utterances, length-sorted mixed (two runs) and with a 3-tile utterance (ticket run)."""
+    2-tile utterances, of 1-tile utterances, length-sorted mixed (two runs) and with 3-tile (cluster of 3) and 6-tile
+    (ticket scheme) utterances."""
     p = ol.default_params(num_banks=40, norm=norm, dyn="acc")
     long_ = synth_utterances(40, 160000, seed=31)
     short = synth_utterances(40, 60000, seed=32)
-    three = synth_utterances(2, 250000, seed=33)
-    for utts in (long_, short, short + long_, short + three + long_):
+    three = synth_utterances(2, 250000, seed=33)          # 3 tiles: cluster of 3
+    six = synth_utterances(1, 450000, seed=34)            # 6 tiles: ticket scheme
+    for utts in (long_, short, short + long_, short + three + long_ + six):
         for extra in (0, afe.BATCH_Q1_EXACT):
             a = run_batch(p, utts, flags=extra)
             b = run_batch(p, utts, flags=extra | afe.BATCH_NO_CLUSTER)
