@@ -151,6 +151,31 @@ class ClockSampler:
                 "samples": len(sm), "samples_in_timed_region": len(inside), "power_w_max": max(power) if power else None}
 
 
+_FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated: with 8 ranks
+    per box the end-to-end path is bound by host memory / PCIe root-complex locality, not by the kernels."""
+    global _FULL_AFFINITY
+    _FULL_AFFINITY = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"bound": True, "cpus": len(cpus), "first_cpu": min(cpus)}
+    except Exception as e:
+        return {"bound": False, "why": str(e)[:120]}
+    return {"bound": False, "why": "empty affinity mask"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -162,6 +187,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(torch, local) if world > 1 and not args.no_numa_bind else {"bound": False, "why": "single rank"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_utts, n = args.utts, SR * SECONDS
@@ -296,7 +322,7 @@ def run_b200(args):
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         e2e = {"value": world * frames / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": int(n_utts * n * 2),
                "d2h_bytes_per_step": int(frames * WIDTH * 4), "ms_per_step": float(et.item()) * 1e3, "steps": e2e_steps,
-               "api": "afe_batch_run_host (pinned host buffers)"}
+               "api": "afe_batch_run_host (pinned host buffers)", "host_affinity": affinity}
         # the host result must be the device result
         chk = h_out[:998 * 4].to(dev)
         step(); torch.cuda.synchronize()
@@ -328,6 +354,8 @@ def run_b200(args):
                 pass
         cpu = None
         if not args.no_cpu:
+            if _FULL_AFFINITY:
+                os.sched_setaffinity(0, _FULL_AFFINITY)   # the CPU baseline uses every host core, not one NUMA node
             threads = os.cpu_count() or 1
             sample = pcm[:64 * n].cpu().numpy().reshape(64, n)
             import oracle_lib as ol
@@ -361,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU (BASELINE config 3: 10000)")
     ap.add_argument("--fast-math", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to their GPU's NUMA node (A/B, N > 1)")
     ap.add_argument("--no-cluster", action="store_true", help="ticket-scheme normalisation instead of clusters + DSMEM (A/B)")
     ap.add_argument("--ws-kernel", action="store_true", help="the warp-specialised persistent k_fused_ws instead of k_fused_mfcc (A/B)")
     ap.add_argument("--no-tma", action="store_true")

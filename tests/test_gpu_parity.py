@@ -302,8 +302,9 @@ def test_batch_cluster_normalisation_equals_ticket_scheme(norm):
     long_ = synth_utterances(40, 160000, seed=31)
     short = synth_utterances(40, 60000, seed=32)
     three = synth_utterances(2, 250000, seed=33)          # 3 tiles: cluster of 3
+    four = synth_utterances(2, 320000, seed=35)           # 4 tiles: cluster of 4 (the largest)
     six = synth_utterances(1, 450000, seed=34)            # 6 tiles: ticket scheme
-    for utts in (long_, short, short + long_, short + three + long_ + six):
+    for utts in (long_, short, short + long_, short + three + four + long_ + six):
         for extra in (0, afe.BATCH_Q1_EXACT):
             a = run_batch(p, utts, flags=extra)
             b = run_batch(p, utts, flags=extra | afe.BATCH_NO_CLUSTER)
