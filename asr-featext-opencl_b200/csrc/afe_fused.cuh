@@ -248,9 +248,12 @@ __device__ __forceinline__ void write_rows(float *__restrict__ orow, const float
 // MODE 1: statistics only  \ a tile that holds a WHOLE utterance (k_fused_ws) takes the statistics first and then writes
 // MODE 2: write (v - mean) * scale, no statistics  / normalised rows directly: no second trip through L2
 // norm3: mean[3] | scale[3] of this thread's three columns (MODE 2 only)
-template <int KIND, int MODE = 0>
-__device__ __forceinline__ void phase3_l3(const FusedArgs &a, const Tile &tl, const float *__restrict__ s_cep, int c0f, int c1f,
-                                          double *__restrict__ s_red3, int tid, int nthreads, int rs, const float *norm3 = nullptr)
+// KIND (statistics: 0 none, 1 sums, 2 + sums of squares, 3 + min/max) is a run-time, warp-uniform argument: one copy of
+// the unrolled block code per MODE keeps the kernel's epilogue small (8 template copies were 6 400 instructions).
+template <int MODE>
+__device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, const Tile &tl, const float *__restrict__ s_cep,
+                                          int c0f, int c1f, double *__restrict__ s_red3, int tid, int nthreads, int rs,
+                                          const float *norm3 = nullptr)
 {
     constexpr int R = 8;
     const int cols = a.cols, width = a.width, T = tl.T, t0 = tl.t0, nout = tl.nout;
@@ -539,11 +542,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         double *s_red3 = reinterpret_cast<double *>(smem + L.off_mags);
         double *s_rec = reinterpret_cast<double *>(smem + L.off_mags + 25 * 1024);
         float *s_mean = reinterpret_cast<float *>(smem + L.off_mags + 30 * 1024), *s_scale = s_mean + width;
-        switch (a.stats_kind) {
-        case 1: dev::phase3_l3<1, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        case 2: dev::phase3_l3<2, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        default: dev::phase3_l3<3, 1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        }
+        dev::phase3_l3<1>(a.stats_kind, a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs);
         __syncthreads();
         if (tid < width) {
             const int rp = kFusedThreads / cols;
@@ -577,18 +576,13 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             const int cc = tid % cols;
             const float norm3[6] = {s_mean[cc], s_mean[cols + cc], s_mean[2 * cols + cc],
                                     s_scale[cc], s_scale[cols + cc], s_scale[2 * cols + cc]};
-            dev::phase3_l3<0, 2>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs, norm3);
+            dev::phase3_l3<2>(0, a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs, norm3);
         }
         dev::cluster_sync(); // no CTA leaves while a peer may still read its record
     } else if (fast3) {
         // default regression: deltas, rows and statistics in one register-blocked pass (dev::phase3_l3)
         double *s_red3 = reinterpret_cast<double *>(smem + L.off_mags);
-        switch (a.stats_kind) {
-        case 0: dev::phase3_l3<0>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        case 1: dev::phase3_l3<1>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        case 2: dev::phase3_l3<2>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        default: dev::phase3_l3<3>(a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs); break;
-        }
+        dev::phase3_l3<0>(a.stats_kind, a, tl, s_cep, c0f, c1f, s_red3, tid, kFusedThreads, rs);
         if (a.partials) {
             __syncthreads();
             if (tid < width) {

@@ -354,11 +354,7 @@ k_fused_ws(const FusedArgs a, const WsSmem L, const __grid_constant__ MelConst m
                 // once and never read back. Same records, same finalisation as the tile-by-tile path below.
                 double *s_rec = reinterpret_cast<double *>(smem + L.off_exch + 25 * 1024);
                 float *s_mean = reinterpret_cast<float *>(smem + L.off_exch + 30 * 1024), *s_scale = s_mean + width;
-                switch (a.stats_kind) {
-                case 1: dev::phase3_l3<1, 1>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-                case 2: dev::phase3_l3<2, 1>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-                default: dev::phase3_l3<3, 1>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-                }
+                dev::phase3_l3<1>(a.stats_kind, a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs);
                 dev::consumer_sync();
                 if (ctid < width) {
                     const int rp = kWsConsumerThreads / cols;
@@ -387,14 +383,9 @@ k_fused_ws(const FusedArgs a, const WsSmem L, const __grid_constant__ MelConst m
                 const int c = ctid % cols;
                 const float norm3[6] = {s_mean[c], s_mean[cols + c], s_mean[2 * cols + c],
                                         s_scale[c], s_scale[cols + c], s_scale[2 * cols + c]};
-                dev::phase3_l3<0, 2>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs, norm3);
+                dev::phase3_l3<2>(0, a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs, norm3);
             } else {
-            switch (a.stats_kind) {
-            case 0: dev::phase3_l3<0>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-            case 1: dev::phase3_l3<1>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-            case 2: dev::phase3_l3<2>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-            default: dev::phase3_l3<3>(a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs); break;
-            }
+            dev::phase3_l3<0>(a.stats_kind, a, tl, s_cep, c0f, c1f, s_red3, ctid, kWsConsumerThreads, rs);
             if (a.partials) {
                 dev::consumer_sync();
                 if (ctid < width) {
