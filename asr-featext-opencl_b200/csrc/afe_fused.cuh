@@ -401,8 +401,9 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                     for (int i = lane; i < n; i += 32) dst[i] = src[i];
                 __syncwarp();
             }
-#pragma unroll 1
-            for (int it = 0; it * FPW < nfw && !(a.debug_skip & 1); it++) {
+#pragma unroll
+            for (int it = 0; it < kWarpFrames / FPW; it++) {
+                if (it * FPW >= nfw || (a.debug_skip & 1)) break;
                 const int fl = it * FPW + fw;                    // frame within the warp's 8 (adjacent frames per call)
                 const int fr = warp * kWarpFrames + fl;          // frame within the round
                 const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
