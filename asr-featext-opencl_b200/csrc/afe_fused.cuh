@@ -467,17 +467,18 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 float2 cep[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) cep[c] = make_float2(0.f, 0.f);
+                // no branch on b < num_banks: the DCT rows of the slots past it are zero (MelConst is zero filled) and their
+                // es is the finite log(1e-30), so the straight-line code lets the constant loads run ahead of the FMAs
+                // (6.23 -> 6.15 ms)
 #pragma unroll
                 for (int k = 0; k < KF; k++) {
                     const int b = warp + k * kFusedWarps;
-                    if (b < a.nb) {
-                        const float2 e2 = make_float2(es[k], es[k]);
+                    const float2 e2 = make_float2(es[k], es[k]);
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            const float4 d4 = mc.dct4[b][c4];
-                            cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
-                            cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
-                        }
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 d4 = mc.dct4[b][c4];
+                        cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
+                        cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
                     }
                 }
                 // partial cepstra of this filter class -> the exchange tile of the warp that will sum column group c4

@@ -298,16 +298,14 @@ k_fused_ws(const FusedArgs a, const WsSmem L, const __grid_constant__ MelConst m
 #pragma unroll
                     for (int c = 0; c < 8; c++) cep[c] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < KF; k++) {
+                    for (int k = 0; k < KF; k++) { // branch free: DCT rows past num_banks are zero, their es is finite
                         const int fb = wc + k * kWsConsumers;
-                        if (fb < a.nb) {
-                            const float2 e2 = make_float2(es[k], es[k]);
+                        const float2 e2 = make_float2(es[k], es[k]);
 #pragma unroll
-                            for (int c4 = 0; c4 < 4; c4++) {
-                                const float4 d4 = mc.dct4[fb][c4];
-                                cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
-                                cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
-                            }
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const float4 d4 = mc.dct4[fb][c4];
+                            cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
+                            cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
                         }
                     }
                     // partial cepstra of this filter class -> the region of the warp that will sum column group c4
