@@ -335,8 +335,7 @@ static FusedArgs make_fused_args(afe_batch *b, const int16_t *d_pcm, float *d_ou
 template <int N2, int NZ, int KF>
 static void launch_fused_ws(afe_batch *b, const FusedArgs &a, int t0, int t1)
 {
-    const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_ws<N2, NZ, true, KF> : k_fused_ws<N2, NZ, false, KF>;
+    auto kern = k_fused_ws<N2, NZ, false, KF>; // AFE_BATCH_FAST_MATH applies to k_fused_mfcc only (halves the build time)
     AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->Lws.total));
     const int ntiles = t1 - t0;
     const int grid = std::min(ntiles, b->sm_count); // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...

@@ -102,3 +102,19 @@ def test_cmvn_finalize_host_formulas(norm):
         np.testing.assert_allclose(scale, 1 / x.std(0, ddof=1), rtol=1e-6)   # unbiased, normalizercpu.cpp:48-49
     if norm == 3:
         np.testing.assert_allclose(scale, 1 / np.maximum(np.abs(x.min(0) - mean), np.abs(x.max(0) - mean)), rtol=1e-6)
+
+
+def test_afe_extract_command_line_errors(tmp_path):
+    """Host driver argument handling needs no GPU: usage / unknown option / unreadable list exit with code 2."""
+    import subprocess
+    exe = os.path.join(ol.ROOT, "asr-featext-opencl_b200", "afe_extract")
+    if not os.path.exists(exe):
+        pytest.skip("afe_extract not built")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "usage: afe_extract" in r.stderr
+    r = subprocess.run([exe, "--no-such-option", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "unknown option" in r.stderr
+    r = subprocess.run([exe, "--scp", str(tmp_path / "missing.scp")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "can't open list" in r.stderr
+    r = subprocess.run([exe, "only_one_file.wav"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2
