@@ -11,30 +11,35 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# AFE_LIB_OVERRIDE: A/B timing of two builds of the same ABI on one box (tools/gpu_ab.sh); never set in production
-LIB_PATH = os.environ.get("AFE_LIB_OVERRIDE") or os.path.join(_HERE, "libafe_cuda.so")
+LIB_PATH = os.path.join(_HERE, "libafe_cuda.so")
+ABI_VERSION = 2
 
 NORM_NONE, NORM_CMN, NORM_CVN, NORM_MINMAX = 0, 1, 2, 3
 DYN_NONE, DYN_DELTA, DYN_ACC = 0, 1, 2
 STATS_REFERENCE_BLOCK, STATS_UTTERANCE, STATS_CORPUS = 0, 1, 2
-BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_FAST_MATH, BATCH_UNFUSED_NORM, BATCH_WS_KERNEL, BATCH_NO_CLUSTER = 1, 2, 4, 8, 16, 32
-OPT_FIX_FLUSH_STATICS = 1
+BATCH_Q1_EXACT, BATCH_NO_TMA, BATCH_UNFUSED_NORM, BATCH_NO_CLUSTER = 1, 2, 8, 32
+OPT_FIX_FLUSH_STATICS, OPT_STAGED_KERNELS = 1, 2
 
 # every symbol include/afe_cuda.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = """
-afe_last_error afe_abi_version afe_device_count afe_estimated_window_count afe_output_width afe_fft_size
+afe_last_error afe_abi_version afe_build_flags afe_device_count afe_estimated_window_count afe_output_width afe_fft_size
 afe_make_window afe_build_filters afe_build_dct
 afe_mfcc_create afe_mfcc_destroy afe_mfcc_set_window afe_mfcc_set_alpha afe_mfcc_input_buffer_size
 afe_mfcc_estimated_window_count afe_mfcc_output_width afe_mfcc_set_input afe_mfcc_flush afe_mfcc_apply
-afe_mfcc_get_output afe_mfcc_reset afe_mfcc_set_option
-afe_segmenter_create afe_segmenter_destroy afe_segmenter_set_window afe_segmenter_set_input afe_segmenter_flush
+afe_mfcc_get_output afe_mfcc_reset afe_mfcc_set_option afe_mfcc_set_preemphasis afe_mfcc_uses_fused_kernel
+afe_mfcc_kernel_launches
+afe_segmenter_create afe_segmenter_destroy afe_segmenter_set_window afe_segmenter_set_preemphasis afe_segmenter_set_input
+afe_segmenter_flush
 afe_segmenter_remaining_samples afe_segmenter_samples afe_segmenter_is_flushed afe_segmenter_was_flushed
 afe_delta_create afe_delta_destroy afe_delta_apply afe_delta_output
-afe_normalizer_create afe_normalizer_destroy afe_normalizer_normalize
+afe_normalizer_create afe_normalizer_destroy afe_normalizer_normalize afe_normalizer_stats_len afe_normalizer_reset
+afe_normalizer_accumulate afe_normalizer_allreduce afe_normalizer_finalize afe_normalizer_apply afe_normalizer_get_stats
+afe_normalizer_set_stats
 afe_device_malloc afe_device_free afe_memcpy_h2d afe_memcpy_d2h
-afe_batch_create afe_batch_destroy afe_batch_set_window afe_batch_set_alpha afe_batch_set_options afe_batch_set_stream
+afe_batch_create afe_batch_destroy afe_batch_set_window afe_batch_set_alpha afe_batch_set_preemphasis afe_batch_set_options
+afe_batch_set_stream
 afe_batch_plan afe_batch_frame_offsets afe_batch_num_tiles afe_batch_kernel_launches afe_batch_kernel_name afe_batch_run_device
-afe_batch_extract_device afe_batch_corpus_stats afe_normalizer_allreduce afe_batch_set_corpus_stats
+afe_batch_extract_device afe_batch_corpus_stats afe_batch_normalizer afe_batch_set_corpus_stats
 afe_batch_normalize_device afe_batch_synchronize afe_batch_run_host
 afe_cmvn_finalize_host afe_shard_utterances afe_nccl_get_unique_id afe_nccl_comm_init afe_nccl_comm_destroy
 """.split()
@@ -75,6 +80,7 @@ def lib():
         sig = {
             "afe_last_error": (C.c_char_p, []),
             "afe_abi_version": (C.c_int, []),
+            "afe_build_flags": (C.c_int, []),
             "afe_device_count": (C.c_int, []),
             "afe_estimated_window_count": (C.c_int, [C.c_int] * 3),
             "afe_output_width": (C.c_int, [pp]),
@@ -95,6 +101,10 @@ def lib():
             "afe_mfcc_get_output": (C.c_int, [vp, fp, C.c_int]),
             "afe_mfcc_reset": (C.c_int, [vp]),
             "afe_mfcc_set_option": (C.c_int, [vp, C.c_int, C.c_int]),
+            "afe_mfcc_set_preemphasis": (C.c_int, [vp, C.c_float]),
+            "afe_mfcc_uses_fused_kernel": (C.c_int, [vp]),
+            "afe_mfcc_kernel_launches": (C.c_int, [vp]),
+            "afe_segmenter_set_preemphasis": (C.c_int, [vp, C.c_float]),
             "afe_segmenter_create": (C.c_int, [C.c_int] * 5 + [C.POINTER(vp)]),
             "afe_segmenter_destroy": (None, [vp]),
             "afe_segmenter_set_window": (C.c_int, [vp, fp]),
@@ -111,6 +121,14 @@ def lib():
             "afe_normalizer_create": (C.c_int, [C.c_int] * 3 + [C.POINTER(vp)]),
             "afe_normalizer_destroy": (None, [vp]),
             "afe_normalizer_normalize": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int]),
+            "afe_normalizer_stats_len": (C.c_int, [vp]),
+            "afe_normalizer_reset": (C.c_int, [vp]),
+            "afe_normalizer_accumulate": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+            "afe_normalizer_allreduce": (C.c_int, [vp, vp]),
+            "afe_normalizer_finalize": (C.c_int, [vp]),
+            "afe_normalizer_apply": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+            "afe_normalizer_get_stats": (C.c_int, [vp, dp]),
+            "afe_normalizer_set_stats": (C.c_int, [vp, dp]),
             "afe_device_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp)]),
             "afe_device_free": (C.c_int, [C.c_int, vp]),
             "afe_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, C.c_size_t]),
@@ -119,6 +137,7 @@ def lib():
             "afe_batch_destroy": (None, [vp]),
             "afe_batch_set_window": (C.c_int, [vp, fp]),
             "afe_batch_set_alpha": (C.c_int, [vp, C.c_float]),
+            "afe_batch_set_preemphasis": (C.c_int, [vp, C.c_float]),
             "afe_batch_set_options": (C.c_int, [vp, C.c_int, C.c_int]),
             "afe_batch_set_stream": (C.c_int, [vp, vp]),
             "afe_batch_plan": (C.c_int, [vp, i64p, i64p, C.c_int, i64p]),
@@ -129,7 +148,7 @@ def lib():
             "afe_batch_run_device": (C.c_int, [vp, vp, vp]),
             "afe_batch_extract_device": (C.c_int, [vp, vp, vp]),
             "afe_batch_corpus_stats": (C.c_int, [vp, C.POINTER(vp), ip]),
-            "afe_normalizer_allreduce": (C.c_int, [vp, vp]),
+            "afe_batch_normalizer": (vp, [vp]),
             "afe_batch_set_corpus_stats": (C.c_int, [vp, dp, C.c_int]),
             "afe_batch_normalize_device": (C.c_int, [vp, vp]),
             "afe_batch_synchronize": (C.c_int, [vp]),
@@ -226,6 +245,17 @@ class MfccCuda:
     def set_alpha(self, alpha):
         _check(lib().afe_mfcc_set_alpha(self._h, float(alpha)))
 
+    def set_preemphasis(self, coefficient):
+        _check(lib().afe_mfcc_set_preemphasis(self._h, float(coefficient)))
+
+    @property
+    def uses_fused_kernel(self):
+        return bool(lib().afe_mfcc_uses_fused_kernel(self._h))
+
+    @property
+    def kernel_launches(self):
+        return lib().afe_mfcc_kernel_launches(self._h)
+
     def get_input_buffer_size(self):
         return lib().afe_mfcc_input_buffer_size(self._h)
 
@@ -261,12 +291,17 @@ class MfccCuda:
         _check(lib().afe_mfcc_set_option(self._h, int(option), int(value)))
 
 
-def extract_stream(params, pcm, alpha=1.0, window=None, cuda_device=0, fix_flush_statics=False):
+def extract_stream(params, pcm, alpha=1.0, window=None, cuda_device=0, fix_flush_statics=False, preemphasis=0.0,
+                   staged=False):
     """The reference driver's block loop (ASR_OCL.cpp:227-301) over one utterance, through the streaming object."""
     m = MfccCuda(params, cuda_device)
     try:
+        if staged:
+            m.set_option(OPT_STAGED_KERNELS, 1)
         m.set_window(make_window(params.window_size) if window is None else window)
         m.set_alpha(alpha)
+        if preemphasis:
+            m.set_preemphasis(preemphasis)
         if fix_flush_statics:
             m.set_option(OPT_FIX_FLUSH_STATICS, 1)
         limit = m.get_input_buffer_size()
@@ -413,11 +448,54 @@ class NormalizerCuda:
         buf.free()
         return out
 
+    # ---- corpus-level verbs on the running record (sum | sumsq | count | min | max): reset -> accumulate* -> allreduce ->
+    #      finalize -> apply*. Host arrays are uploaded here for convenience; the C ABI takes device pointers.
+    @property
+    def stats_len(self):
+        return lib().afe_normalizer_stats_len(self._h)
+
+    def reset(self):
+        _check(lib().afe_normalizer_reset(self._h))
+
+    def accumulate(self, data):
+        data = np.ascontiguousarray(data, np.float32)
+        buf = DeviceBuffer(max(data.nbytes, 4), self.dev)
+        buf.upload(data)
+        _check(lib().afe_normalizer_accumulate(self._h, buf.ptr, 0, data.shape[0]))
+        self.get_stats()          # drains the stream before the buffer goes away
+        buf.free()
+
+    def allreduce(self, nccl_comm):
+        _check(lib().afe_normalizer_allreduce(self._h, C.c_void_p(nccl_comm)))
+
+    def finalize(self):
+        _check(lib().afe_normalizer_finalize(self._h))
+
+    def apply(self, data):
+        data = np.ascontiguousarray(data, np.float32)
+        buf = DeviceBuffer(max(data.nbytes, 4), self.dev)
+        buf.upload(data)
+        _check(lib().afe_normalizer_apply(self._h, buf.ptr, 0, data.shape[0]))
+        out = buf.download(data.shape, np.float32)
+        buf.free()
+        return out
+
+    def get_stats(self):
+        s = np.zeros(self.stats_len, np.float64)
+        _check(lib().afe_normalizer_get_stats(self._h, s.ctypes.data_as(C.POINTER(C.c_double))))
+        return s
+
+    def set_stats(self, stats):
+        s = np.ascontiguousarray(stats, np.float64)
+        assert len(s) == self.stats_len
+        _check(lib().afe_normalizer_set_stats(self._h, s.ctypes.data_as(C.POINTER(C.c_double))))
+
 
 class BatchMfcc:
     """Fused batch extractor (afe_batch_*): whole utterances, one fused kernel + a light normalise pass."""
 
-    def __init__(self, params, cuda_device=0, stats_scope=STATS_REFERENCE_BLOCK, flags=0, window=None, alpha=1.0):
+    def __init__(self, params, cuda_device=0, stats_scope=STATS_REFERENCE_BLOCK, flags=0, window=None, alpha=1.0,
+                 preemphasis=0.0):
         self._h = C.c_void_p()
         self.params, self.dev = params, cuda_device
         _check(lib().afe_batch_create(C.byref(params), cuda_device, C.byref(self._h)))
@@ -426,6 +504,8 @@ class BatchMfcc:
         w = make_window(params.window_size) if window is None else np.ascontiguousarray(window, np.float32)
         _check(lib().afe_batch_set_window(self._h, _fp(w)))
         _check(lib().afe_batch_set_alpha(self._h, float(alpha)))
+        if preemphasis:
+            _check(lib().afe_batch_set_preemphasis(self._h, float(preemphasis)))
         self.frame_offsets = None
 
     def close(self):
@@ -480,8 +560,24 @@ class BatchMfcc:
         _check(lib().afe_batch_corpus_stats(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    @property
+    def normalizer(self):
+        """afe_normalizer* that owns the corpus record (scope CORPUS, after plan)."""
+        h = lib().afe_batch_normalizer(self._h)
+        if not h:
+            raise AfeError("the batch has no corpus Normalizer (scope != CORPUS, norm == NONE or not planned)")
+        return h
+
     def allreduce(self, nccl_comm):
-        _check(lib().afe_normalizer_allreduce(self._h, C.c_void_p(nccl_comm)))
+        """The one collective of the path, inside the Normalizer subsystem."""
+        _check(lib().afe_normalizer_allreduce(C.c_void_p(self.normalizer), C.c_void_p(nccl_comm)))
+
+    def corpus_record(self):
+        """HOST copy of the corpus record (after corpus_stats / allreduce)."""
+        n = C.c_void_p(self.normalizer)
+        s = np.zeros(lib().afe_normalizer_stats_len(n), np.float64)
+        _check(lib().afe_normalizer_get_stats(n, s.ctypes.data_as(C.POINTER(C.c_double))))
+        return s
 
     def set_corpus_stats(self, stats):
         s = np.ascontiguousarray(stats, np.float64)

@@ -1,5 +1,6 @@
 // Batch extractor (afe_batch_*): planning, launch of the fused kernel K1, statistics finalize K2 and the normalise
-// pass K3, plus the corpus-CMVN exchange hooks of the Normalizer subsystem.
+// pass K3. Corpus-level statistics are owned by a Normalizer object (afe_batch_normalizer): the batch reduces its
+// per-tile records into the Normalizer's record, the Normalizer all-reduces it over NCCL, the batch normalises with it.
 #include <algorithm>
 #include <atomic>
 #include <memory>
@@ -8,8 +9,7 @@
 #include <cstring>
 
 #include "afe_internal.h"
-#include "afe_fused.cuh"
-#include "afe_fused_ws.cuh"
+#include "afe_fused_host.h"
 #include "afe_nccl.h"
 
 namespace afe {
@@ -142,136 +142,54 @@ __global__ void k_finalize_stats(const double *__restrict__ stats, int width, in
     scale[(long long)g * width + c] = sc;
 }
 
-// K3: in-place (x - mean) [* scale] over one tile's rows: 128-bit accesses on the 16-byte aligned body of the tile's
-// contiguous region, columns tracked incrementally (no division in the loop). HBM bound: 8 B per float.
+// K3: in-place (x - mean) [* scale] over one tile's rows (dev::normalise_tile_rows). HBM / L2 bound: 8 B per float.
 __global__ void k_normalize_tiles(float *__restrict__ out, const Tile *__restrict__ tiles, int width, int norm_type,
                                   const float *__restrict__ mean, const float *__restrict__ scale)
 {
     extern __shared__ float s_ms[]; // mean[width] | scale[width]
-    const Tile tl = tiles[blockIdx.x];
-    float *base = out + (tl.out_row0 + tl.t0) * (long long)width;
-    const int n = tl.nout * width;
-    for (int i = threadIdx.x; i < width; i += blockDim.x) {
-        s_ms[i] = mean[(long long)tl.group * width + i];
-        s_ms[width + i] = norm_type == AFE_NORM_CMN ? 1.f : scale[(long long)tl.group * width + i];
-    }
-    __syncthreads();
-    const float *m = s_ms, *sc = s_ms + width;
-    const bool cmn = norm_type == AFE_NORM_CMN;
-    const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) >> 2));
-    const int n4 = (n - head) >> 2, tail0 = head + 4 * n4;
-    if ((int)threadIdx.x < head) {
-        const int i = threadIdx.x;
-        const float v = base[i] - m[i % width];
-        base[i] = cmn ? v : v * sc[i % width];
-    }
-    if ((int)threadIdx.x < n - tail0) {
-        const int i = tail0 + threadIdx.x, c = i % width;
-        const float v = base[i] - m[c];
-        base[i] = cmn ? v : v * sc[c];
-    }
-    float4 *p4 = reinterpret_cast<float4 *>(base + head);
-    int c = (head + 4 * (int)threadIdx.x) % width;
-    const int cstep = (4 * (int)blockDim.x) % width;
-    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
-        float4 v = p4[j];
-        int c1 = c + 1; if (c1 >= width) c1 -= width;
-        int c2 = c1 + 1; if (c2 >= width) c2 -= width;
-        int c3 = c2 + 1; if (c3 >= width) c3 -= width;
-        v.x -= m[c]; v.y -= m[c1]; v.z -= m[c2]; v.w -= m[c3];
-        if (!cmn) { v.x *= sc[c]; v.y *= sc[c1]; v.z *= sc[c2]; v.w *= sc[c3]; }
-        p4[j] = v;
-        c += cstep; if (c >= width) c -= width;
-    }
+    dev::normalise_tile_rows(out, tiles[blockIdx.x], width, norm_type, mean, scale, s_ms);
 }
 
-constexpr int kCorpusBlocks = 296; // 2 per SM
 static std::atomic<int> g_launches{0};
 int kernel_launch_count() { return g_launches.load(); }
 void count_launch(int n) { g_launches.fetch_add(n); }
 
-} // namespace afe
+// ------------------------------------------------------------------------------------------------ K1 launch table
+#define AFE_DECL_INST(k) cudaError_t fused_launch_##k(const FusedLaunch &); int fused_max_clusters_##k(const FusedLaunch &);
+AFE_DECL_INST(0) AFE_DECL_INST(1) AFE_DECL_INST(2) AFE_DECL_INST(3) AFE_DECL_INST(4) AFE_DECL_INST(5)
+AFE_DECL_INST(6) AFE_DECL_INST(7) AFE_DECL_INST(8) AFE_DECL_INST(9) AFE_DECL_INST(10) AFE_DECL_INST(11)
+#undef AFE_DECL_INST
 
-using namespace afe;
-
-// ================================================================================================== afe_batch
-struct afe_batch {
-    Derived d;
-    int device;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    FftTables fft;
-    MelTables mel;
-    float alpha = 1.f;
-    bool window_set = false;
-    int scope = AFE_STATS_REFERENCE_BLOCK, flags = 0;
-    // plan
-    int n_utts = 0, n_tiles = 0, n_groups = 0;
-    bool aligned = false;
-    std::vector<int64_t> sample_off, sample_len, frame_off;
-    std::vector<int> h_tile_begin;          // [n_utts+1] first tile of every utterance
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_k;
-    int64_t pcm_extent = 0;
-    Tile *d_tiles = nullptr;
-    int *d_tile_begin = nullptr;
-    double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr, *d_scratch = nullptr;
-    int *d_counters = nullptr;
-    int *d_scratch_begin = nullptr;
-    float *d_mean = nullptr, *d_scale = nullptr;
-    int tc_max = 0, nout_max = 0;
-    const int warps = 8;      // warps per CTA of the fused kernel
-    int max_tiles_per_utt = 0;
-    // In-kernel normalisation lets ONE tile normalise its whole utterance: right for short utterances, a serial
-    // bottleneck for a long stream (config 5: 720 tiles) -> those batches take the K2 + K3 kernels.
-    bool fuse_norm() const { return !(flags & AFE_BATCH_UNFUSED_NORM) && max_tiles_per_utt <= 8; }
-    FusedSmem L{};
-    WsSmem Lws{};             // layout of the warp-specialised kernel (k_fused_ws)
-    int sm_count = 0;
-    // k_fused_ws (AFE_BATCH_WS_KERNEL, opt-in) covers the reference's default regression (static + delta + delta-delta,
-    // l1 = l2 = 3); everything else takes k_fused_mfcc. Decided at plan time: the two kernels tile differently.
-    bool ws_eligible() const { return (flags & AFE_BATCH_WS_KERNEL) && d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3; }
-    bool ws_planned = false;
-    bool use_ws() const { return ws_planned; }
-    MelConst mc;
-    float mc_alpha = -1.f;
-    int last_launches = 0;
-    // host staging for run_host
-    int16_t *d_pcm_stage = nullptr; float *d_out_stage = nullptr;
-    size_t pcm_stage_bytes = 0, out_stage_bytes = 0;
-
-    explicit afe_batch(const afe_params &p, int dev) : d(p), device(dev) {}
-    void free_plan()
-    {
-        if (d_tiles) cudaFree(d_tiles);
-        if (d_tile_begin) cudaFree(d_tile_begin);
-        if (d_counts) cudaFree(d_counts);
-        if (d_partials) cudaFree(d_partials);
-        if (d_stats) cudaFree(d_stats);
-        if (d_scratch) cudaFree(d_scratch);
-        if (d_counters) cudaFree(d_counters);
-        d_counters = nullptr;
-        if (d_scratch_begin) cudaFree(d_scratch_begin);
-        d_scratch = nullptr; d_scratch_begin = nullptr;
-        if (d_mean) cudaFree(d_mean);
-        if (d_scale) cudaFree(d_scale);
-        d_tiles = nullptr; d_tile_begin = nullptr; d_counts = d_partials = d_stats = nullptr; d_mean = d_scale = nullptr;
-    }
-};
-
-static void check_fused_support(const Derived &d)
+cudaError_t launch_fused_variant(int key, const FusedLaunch &fl)
 {
-    if (d.N2 != 512 && d.N2 != 256)
-        throw Error("fused batch path supports 256/512-point FFTs (window_size 129..512); use the streaming object");
-    if (d.S % 2) throw Error("fused batch path needs an even shift");
-    if (d.dct_len > 16) throw Error("fused batch path supports ceps_len + c0 <= 16");
-    if (d.width > 128) throw Error("fused batch path supports output width <= 128");
-    if (d.nb > kMaxBanks) throw Error("fused batch path supports num_banks <= 64");
+    typedef cudaError_t (*fn_t)(const FusedLaunch &);
+    static const fn_t table[kFusedVariants] = {fused_launch_0, fused_launch_1, fused_launch_2,  fused_launch_3,
+                                               fused_launch_4, fused_launch_5, fused_launch_6,  fused_launch_7,
+                                               fused_launch_8, fused_launch_9, fused_launch_10, fused_launch_11};
+    if (key < 0 || key >= kFusedVariants) return cudaErrorInvalidValue;
+    return table[key](fl);
+}
+int fused_variant_max_clusters(int key, const FusedLaunch &fl)
+{
+    typedef int (*fn_t)(const FusedLaunch &);
+    static const fn_t table[kFusedVariants] = {fused_max_clusters_0, fused_max_clusters_1, fused_max_clusters_2,
+                                               fused_max_clusters_3, fused_max_clusters_4, fused_max_clusters_5,
+                                               fused_max_clusters_6, fused_max_clusters_7, fused_max_clusters_8,
+                                               fused_max_clusters_9, fused_max_clusters_10, fused_max_clusters_11};
+    if (key < 0 || key >= kFusedVariants) return -1;
+    return table[key](fl);
 }
 
-template <int N2> static FusedSmem layout_for(const afe_batch *b)
+// ------------------------------------------------------------------------------------------------ FusedEngine
+std::string fused_unsupported_reason(const Derived &d)
 {
-    const Derived &d = b->d;
-    return fused_smem_layout<N2>(b->warps, d.S, d.cols, b->tc_max, b->nout_max, d.l2, d.width / d.cols);
+    if (d.N2 != 512 && d.N2 != 256) return "fused path supports 256/512-point FFTs (window_size 129..512)";
+    if (d.S % 2) return "fused path needs an even shift";
+    if (d.dct_len > 16) return "fused path supports ceps_len + c0 <= 16";
+    if (d.width > 128) return "fused path supports output width <= 128";
+    if (d.nb > kMaxBanks) return "fused path supports num_banks <= 64";
+    if (d.W > 26 * (d.M / 16) && d.W > d.N2) return "window longer than the FFT";
+    return "";
 }
 
 // Mel weights + DCT matrix as a by-value kernel parameter (constant bank). Per filter b: bins [edges[b], edges[b+2]) with
@@ -305,129 +223,244 @@ static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
     }
 }
 
-static FusedArgs make_fused_args(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, bool fuse_norm)
+FusedEngine::FusedEngine(const Derived &dd, int dev) : d(dd), device(dev)
 {
-    const Derived &d = b->d;
+    const std::string why = fused_unsupported_reason(d);
+    if (!why.empty()) throw Error(why);
+    sm_count = sm_count_of(dev);
+    fft.build(d.N2);
+    // tile geometry (2 CTAs per SM): the cepstra tile holds up to 512 frames (<= 27 KB of shared memory)
+    int tc = 512;
+    tc = std::min(tc, (6912 / d.cols) / kRoundFrames * kRoundFrames);
+    tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
+    tc_max = tc; nout_max = tc - 2 * d.D;
+    const int ns = d.width / d.cols;
+    L = d.N2 == 512 ? fused_smem_layout<512>(8, d.S, d.cols, tc_max, nout_max, d.l2, ns)
+                    : fused_smem_layout<256>(8, d.S, d.cols, tc_max, nout_max, d.l2, ns);
+    if (L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
+    const int R = d.M / 16;
+    const bool pruned = d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
+    const int kf = (d.nb + 7) / 8;     // filters per warp (8 warps): instantiated for 3, 5 and 8
+    key = (d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
+}
+FusedEngine::~FusedEngine() { fft.release(); mel.release(); }
+
+void FusedEngine::set_window(const float *window, cudaStream_t st)
+{
+    upload_window(d, window, mel, st);
+    window_set = true;
+}
+void FusedEngine::ensure_mel(float alpha)
+{
+    if (mc_alpha != alpha) { build_mel_const(d, alpha, mc); mc_alpha = alpha; }
+}
+
+int FusedEngine::plan_rows(std::vector<Tile> &tiles, long long pcm_off, long long out_row0, int T, int t_first, int n_out,
+                           int group) const
+{
+    if (n_out <= 0) return 0;
+    // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
+    int ntile = (n_out + nout_max - 1) / nout_max, best_cost = 1 << 30;
+    for (int cand = ntile; cand <= ntile + 3; cand++) {
+        const int no = (n_out + cand - 1) / cand;
+        int cost = 0;
+        for (int t0 = t_first; t0 < t_first + n_out; t0 += no) {
+            const int c0 = std::max(0, t0 - d.D), c1 = std::min(T, t0 + std::min(no, t_first + n_out - t0) + d.D);
+            cost += (c1 - c0 + kRoundFrames - 1) / kRoundFrames;
+        }
+        if (cost < best_cost) { best_cost = cost; ntile = cand; }
+    }
+    const int nout = (n_out + ntile - 1) / ntile, first = (int)tiles.size(), count = (n_out + nout - 1) / nout;
+    for (int t0 = t_first; t0 < t_first + n_out; t0 += nout) {
+        Tile tl;
+        tl.pcm_off = pcm_off; tl.out_row0 = out_row0; tl.T = T; tl.t0 = t0;
+        tl.nout = std::min(nout, t_first + n_out - t0); tl.group = group;
+        tl.tile0 = first; tl.ntiles = count;
+        tiles.push_back(tl);
+    }
+    return count;
+}
+
+FusedArgs FusedEngine::base_args(int q1, bool use_tma) const
+{
     FusedArgs a{};
-    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles; a.tile_base = t0;
-    a.window2 = b->mel.d_window2; a.tw_a = b->fft.d_tw_a; a.tw_p = b->fft.d_tw_p;
-    a.partials = want_stats ? b->d_partials : nullptr;
-    a.counters = (want_stats && fuse_norm) ? b->d_counters : nullptr;
+    a.window2 = mel.d_window2; a.tw_a = fft.d_tw_a; a.tw_p = fft.d_tw_p;
     a.norm_type = d.p.norm; a.norm_after_dyn = d.p.norm_after_dyn;
     a.W = d.W; a.S = d.S; a.nb = d.nb; a.dct_len = d.C > 0 ? d.dct_len : 0; a.cols = d.cols; a.width = d.width;
     a.l1 = d.l1; a.l2 = d.l2; a.nstreams = d.width / d.cols;
-    a.q1 = (b->flags & AFE_BATCH_Q1_EXACT) && d.D > 0 ? 1 : 0;
-    a.use_tma = (b->aligned && !(b->flags & AFE_BATCH_NO_TMA) && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0) ? 1 : 0;
-    if (!want_stats) a.stats_rows_mode = 0;
-    else if (!d.p.norm_after_dyn) a.stats_rows_mode = 2;
-    else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
-    a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
-    a.tc_max = b->tc_max;
-    { const char *dbg = getenv("AFE_DEBUG_SKIP"); a.debug_skip = dbg ? atoi(dbg) : 0; }
+    a.q1 = d.D > 0 ? q1 : 0;
+    a.use_tma = use_tma ? 1 : 0;
+    a.tc_max = tc_max;
+    a.pre = pre;
     float den1 = 0, den2 = 0;
     for (int l = 1; l <= d.l1; l++) den1 += l * l;   // float accumulation like deltacpu.cpp:26
     for (int l = 1; l <= d.l2; l++) den2 += l * l;
     a.rden1 = den1 > 0 ? 1.f / (2 * den1) : 0.f;
     a.rden2 = den2 > 0 ? 1.f / (2 * den2) : 0.f;
+#ifdef AFE_DEVTOOLS
+    { const char *dbg = getenv("AFE_DEBUG_SKIP"); a.debug_skip = dbg ? atoi(dbg) : 0; }
+#endif
     return a;
 }
 
-template <int N2, int NZ, int KF>
-static void launch_fused_ws(afe_batch *b, const FusedArgs &a, int t0, int t1)
+// A clustered launch needs all CTAs of a cluster co-scheduled (111 KB of shared memory each). On a partitioned device
+// (MIG / MPS slices, fewer GPCs) that can be impossible: probe once per cluster size and let the caller use the ticket scheme.
+bool FusedEngine::cluster_schedulable(int cluster, const FusedArgs &a, cudaStream_t st)
 {
-    auto kern = k_fused_ws<N2, NZ, false, KF>; // AFE_BATCH_FAST_MATH applies to k_fused_mfcc only (halves the build time)
-    AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->Lws.total));
-    const int ntiles = t1 - t0;
-    const int grid = std::min(ntiles, b->sm_count); // persistent: one CTA per SM walks tiles blockIdx.x, +grid, ...
-    kern<<<grid, kWsThreads, b->Lws.total, b->stream>>>(a, b->Lws, b->mc, ntiles);
-    AFE_CUDA(cudaGetLastError());
-    count_launch();
-    b->last_launches++;
-}
-
-// cluster: 0 = plain launch (ticket scheme or no fused normalisation); 1, 2, ... = clustered launch, one cluster per
-// utterance of `cluster` tiles, normalisation inside the cluster (FusedArgs::cluster_norm)
-template <int N2, int NZ, int WARPS, int KF>
-static void launch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm,
-                         int cluster = 0)
-{
-    FusedArgs a = make_fused_args(b, d_pcm, d_out, want_stats, t0, fuse_norm);
-    if (b->use_ws()) { launch_fused_ws<N2, NZ, KF>(b, a, t0, t1); return; }
-    const bool fast = (b->flags & AFE_BATCH_FAST_MATH) != 0;
-    auto kern = fast ? k_fused_mfcc<N2, NZ, true, WARPS, KF> : k_fused_mfcc<N2, NZ, false, WARPS, KF>;
-    AFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.total));
-    if (cluster > 0) {
-        a.cluster_norm = 1;
-        a.counters = nullptr;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(t1 - t0); cfg.blockDim = dim3(32 * WARPS); cfg.dynamicSmemBytes = b->L.total; cfg.stream = b->stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        AFE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b->L, b->mc));
-    } else
-        kern<<<t1 - t0, 32 * WARPS, b->L.total, b->stream>>>(a, b->L, b->mc);
-    AFE_CUDA(cudaGetLastError());
-    count_launch();
-    b->last_launches++;
-}
-
-static void dispatch_fused(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0, int t1, bool fuse_norm,
-                           int cluster)
-{
-    const int R = b->d.M / 16;
-    const bool pruned = b->d.W <= 26 * R; // window tail is zero from n1 = 13 on (400/512 and 200/256 both qualify)
-    const int kf = (b->d.nb + 7) / 8; // filters per warp (8 warps): instantiated for 3, 5 and 8
-    const int key = (b->d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
-    switch (key) {
-    case 0: launch_fused<512, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 1: launch_fused<512, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 2: launch_fused<512, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 3: launch_fused<512, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 4: launch_fused<512, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 5: launch_fused<512, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 6: launch_fused<256, 13, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 7: launch_fused<256, 13, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 8: launch_fused<256, 13, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 9: launch_fused<256, 16, 8, 3>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    case 10: launch_fused<256, 16, 8, 5>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
-    default: launch_fused<256, 16, 8, 8>(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, cluster); break;
+    if (cluster < 1 || cluster > 4) return false;
+    if (cluster_probe[cluster] < 0) {
+        FusedLaunch fl{a, L, &mc, cluster, cluster, st};
+        const int n = fused_variant_max_clusters(key, fl);
+        cluster_probe[cluster] = n > 0 ? n : 0;
     }
+    return cluster_probe[cluster] > 0;
 }
 
-// Tiles [t0, t1) (whole utterances). With fused normalisation and the default regression the utterances are taken in
-// runs of equal tile count and every run of utterances with 1 to kMaxClusterTiles tiles becomes ONE clustered launch (cluster = utterance);
-// a batch that would need more than kMaxClusterRuns launches (ragged lengths in random order) or other tile counts keeps
-// the ticket scheme (last tile normalises through L2) in a single launch.
+void FusedEngine::launch(const FusedArgs &a, int grid, int cluster, cudaStream_t st)
+{
+    if (!window_set) throw Error("set_window must be called before running");
+    FusedLaunch fl{a, L, &mc, grid, cluster, st};
+    const cudaError_t e = launch_fused_variant(key, fl);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at k_fused_mfcc launch" + (cluster > 0 ? " (clustered)" : ""));
+    }
+    count_launch();
+}
+
+} // namespace afe
+
+using namespace afe;
+
+// ================================================================================================== afe_batch
+struct afe_batch {
+    Derived d;
+    int device;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::unique_ptr<FusedEngine> eng;
+    float alpha = 1.f;
+    int scope = AFE_STATS_REFERENCE_BLOCK, flags = 0;
+    // plan
+    int n_utts = 0, n_tiles = 0, n_groups = 0;
+    bool aligned = false;
+    std::vector<int64_t> sample_off, sample_len, frame_off;
+    std::vector<int> h_tile_begin;          // [n_utts+1] first tile of every utterance
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
+    int64_t pcm_extent = 0;
+    Tile *d_tiles = nullptr;
+    int *d_tile_begin = nullptr;
+    double *d_counts = nullptr, *d_partials = nullptr, *d_stats = nullptr, *d_scratch = nullptr;
+    int *d_counters = nullptr;      // [n_groups] arrival tickets + [1] role tickets of the long-utterance scheme
+    unsigned *d_flags = nullptr;    // [n_groups]
+    unsigned epoch = 0;
+    int *d_scratch_begin = nullptr;
+    float *d_mean = nullptr, *d_scale = nullptr;
+    int corpus_blocks = 0;          // level-1 blocks of the corpus reduction (2 per SM)
+    afe_normalizer *cnorm = nullptr; // corpus scope: the Normalizer that owns the record (d_stats aliases its buffer)
+    int max_tiles_per_utt = 0;
+    // One tile normalising its whole utterance is right for short utterances and a serial bottleneck for long ones:
+    // up to 8 tiles -> clusters / ticket scheme; more -> the role scheme (normaliser CTAs, one per tile, same launch).
+    bool fuse_norm() const { return !(flags & AFE_BATCH_UNFUSED_NORM); }
+    bool long_scheme() const { return max_tiles_per_utt > 8; }
+    int last_launches = 0;
+    // host staging for run_host
+    int16_t *d_pcm_stage = nullptr; float *d_out_stage = nullptr;
+    size_t pcm_stage_bytes = 0, out_stage_bytes = 0;
+
+    explicit afe_batch(const afe_params &p, int dev) : d(p), device(dev) {}
+    void free_plan()
+    {
+        if (d_tiles) cudaFree(d_tiles);
+        if (d_tile_begin) cudaFree(d_tile_begin);
+        if (d_counts) cudaFree(d_counts);
+        if (d_partials) cudaFree(d_partials);
+        if (d_stats && !cnorm) cudaFree(d_stats);
+        if (d_scratch) cudaFree(d_scratch);
+        if (d_counters) cudaFree(d_counters);
+        if (d_flags) cudaFree(d_flags);
+        if (d_scratch_begin) cudaFree(d_scratch_begin);
+        if (d_mean) cudaFree(d_mean);
+        if (d_scale) cudaFree(d_scale);
+        if (cnorm) { cnorm->st = nullptr; afe_normalizer_destroy(cnorm); cnorm = nullptr; }
+        d_tiles = nullptr; d_tile_begin = nullptr; d_counts = d_partials = d_stats = d_scratch = nullptr;
+        d_counters = nullptr; d_flags = nullptr; d_scratch_begin = nullptr; d_mean = d_scale = nullptr;
+    }
+};
+
+static FusedArgs make_fused_args(afe_batch *b, const int16_t *d_pcm, float *d_out, bool want_stats, int t0)
+{
+    const Derived &d = b->d;
+    const bool tma = b->aligned && !(b->flags & AFE_BATCH_NO_TMA) && (reinterpret_cast<uintptr_t>(d_pcm) & 15) == 0;
+    FusedArgs a = b->eng->base_args((b->flags & AFE_BATCH_Q1_EXACT) ? 1 : 0, tma);
+    a.pcm = d_pcm; a.out = d_out; a.tiles = b->d_tiles; a.tile_base = t0;
+    a.partials = want_stats ? b->d_partials : nullptr;
+    if (!want_stats) a.stats_rows_mode = 0;
+    else if (!d.p.norm_after_dyn) a.stats_rows_mode = 2;
+    else a.stats_rows_mode = b->scope == AFE_STATS_REFERENCE_BLOCK ? 1 : 2;
+    a.stats_kind = !want_stats ? 0 : (d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3);
+    return a;
+}
+
+// Tiles [t0, t1) (whole utterances) through K1. With fused normalisation:
+//  * the default regression and utterances of 1..4 tiles: runs of equal tile count become ONE clustered launch each
+//    (cluster = utterance, statistics through distributed shared memory), at most kMaxClusterRuns launches;
+//  * other batches whose utterances have at most 8 tiles: the ticket scheme (last tile normalises through L2), one launch;
+//  * batches with longer utterances: the role scheme (2 x tiles CTAs, the second half normalises a tile each), one launch.
 constexpr int kMaxClusterRuns = 8;
 constexpr int kMaxClusterTiles = 4; // utterances of up to 4 tiles (~20 s) form a cluster; longer ones keep the ticket scheme
 static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0 = 0, int t1 = -1, bool fuse_norm = false)
 {
     if (t1 < 0) t1 = b->n_tiles;
     if (t1 <= t0) return;
-    if (!b->window_set) throw Error("set_window must be called before running");
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
-    if (b->mc_alpha != b->alpha) { build_mel_const(b->d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
+    FusedEngine &eng = *b->eng;
+    eng.ensure_mel(b->alpha);
     const Derived &d = b->d;
     const bool want_stats = d.p.norm != AFE_NORM_NONE;
-    const bool cluster_ok = fuse_norm && want_stats && !b->use_ws() && !(b->flags & AFE_BATCH_NO_CLUSTER) &&
-                            d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
+    FusedArgs a = make_fused_args(b, d_pcm, d_out, want_stats, t0);
+    auto launch = [&](const FusedArgs &args, int grid, int cluster) { eng.launch(args, grid, cluster, b->stream); b->last_launches++; };
+    if (!(fuse_norm && want_stats)) { launch(a, t1 - t0, 0); return; }
+    if (b->long_scheme()) {
+        a.counters = b->d_counters; a.work_counter = b->d_counters + b->n_groups;
+        a.flags = b->d_flags; a.epoch = ++b->epoch; a.ntiles_launch = t1 - t0;
+        a.g_mean = b->d_mean; a.g_scale = b->d_scale;
+        launch(a, 2 * (t1 - t0), 0);
+        return;
+    }
+    const bool cluster_ok = !(b->flags & AFE_BATCH_NO_CLUSTER) && d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
     if (cluster_ok) {
         struct Run { int t0, t1, cluster; };
         std::vector<Run> runs;
         const int u0 = (int)(std::lower_bound(b->h_tile_begin.begin(), b->h_tile_begin.end(), t0) - b->h_tile_begin.begin());
+        bool schedulable = true;
         for (int u = u0; u < b->n_utts && b->h_tile_begin[u] < t1 && (int)runs.size() <= kMaxClusterRuns; u++) {
             const int nt = b->h_tile_begin[u + 1] - b->h_tile_begin[u], cl = nt <= kMaxClusterTiles ? nt : 0;
+            if (cl > 0 && !eng.cluster_schedulable(cl, a, b->stream)) { schedulable = false; break; }
             if (!runs.empty() && runs.back().cluster == cl) runs.back().t1 = b->h_tile_begin[u + 1];
             else runs.push_back({b->h_tile_begin[u], b->h_tile_begin[u + 1], cl});
         }
-        if ((int)runs.size() <= kMaxClusterRuns && !runs.empty() && runs.front().t0 == t0 && runs.back().t1 == t1) {
-            for (const Run &r : runs) dispatch_fused(b, d_pcm, d_out, want_stats, r.t0, r.t1, fuse_norm, r.cluster);
+        if (schedulable && (int)runs.size() <= kMaxClusterRuns && !runs.empty() && runs.front().t0 == t0 && runs.back().t1 == t1) {
+            for (const Run &r : runs) {
+                FusedArgs ar = a;
+                ar.tile_base = r.t0;
+                if (r.cluster > 0) { ar.cluster_norm = 1; ar.counters = nullptr; }
+                else ar.counters = b->d_counters;
+                try {
+                    launch(ar, r.t1 - r.t0, r.cluster);
+                } catch (const Error &) {
+                    if (r.cluster == 0) throw;
+                    // the clustered launch was refused (nothing ran): this run takes the ticket scheme instead
+                    eng.cluster_probe[r.cluster] = 0;
+                    ar.cluster_norm = 0; ar.counters = b->d_counters;
+                    launch(ar, r.t1 - r.t0, 0);
+                }
+            }
             return;
         }
     }
-    dispatch_fused(b, d_pcm, d_out, want_stats, t0, t1, fuse_norm, 0);
+    a.counters = b->d_counters;
+    launch(a, t1 - t0, 0);
 }
 
 static void run_reduce(afe_batch *b, int g0 = 0, int g1 = -1)
@@ -435,8 +468,8 @@ static void run_reduce(afe_batch *b, int g0 = 0, int g1 = -1)
     if (g1 < 0) g1 = b->n_groups;
     if (g1 <= g0) return;
     const int w = b->d.width;
-    if (b->scope == AFE_STATS_CORPUS && b->n_tiles > 2 * kCorpusBlocks) {
-        k_reduce_partials_level1<<<kCorpusBlocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, w, b->d_scratch);
+    if (b->scope == AFE_STATS_CORPUS && b->n_tiles > 2 * b->corpus_blocks) {
+        k_reduce_partials_level1<<<b->corpus_blocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, w, b->d_scratch);
         AFE_CUDA(cudaGetLastError());
         k_reduce_partials<<<1, 128, 0, b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, w, b->d_stats);
         AFE_CUDA(cudaGetLastError());
@@ -476,17 +509,27 @@ int afe_device_count(void)
     return n;
 }
 
+int afe_build_flags(void)
+{
+#ifdef AFE_DEVTOOLS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out)
 {
     *out = nullptr;
     return guarded([&] {
         if (afe_device_count() <= cuda_device) throw Error("no usable CUDA device " + std::to_string(cuda_device) + " (the product has no CPU fallback)");
         std::unique_ptr<afe_batch> b(new afe_batch(*p, cuda_device));
-        check_fused_support(b->d);
+        const std::string why = fused_unsupported_reason(b->d);
+        if (!why.empty()) throw Error(why + "; use the streaming object");
         DeviceGuard g(cuda_device);
         AFE_CUDA(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
         b->stream = b->own_stream;
-        b->fft.build(b->d.N2);
+        b->eng.reset(new FusedEngine(b->d, cuda_device));
         *out = b.release();
     });
 }
@@ -497,7 +540,7 @@ void afe_batch_destroy(afe_batch *b)
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     b->free_plan();
-    b->fft.release(); b->mel.release();
+    b->eng.reset();
     if (b->d_pcm_stage) cudaFree(b->d_pcm_stage);
     if (b->d_out_stage) cudaFree(b->d_out_stage);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -510,28 +553,33 @@ void afe_batch_destroy(afe_batch *b)
 
 int afe_batch_set_window(afe_batch *b, const float *window)
 {
-    return guarded([&] {
-        DeviceGuard g(b->device);
-        upload_window(b->d, window, b->mel, b->stream);
-        b->window_set = true;
-    });
+    return guarded([&] { DeviceGuard g(b->device); b->eng->set_window(window, b->stream); });
 }
 
 int afe_batch_set_alpha(afe_batch *b, float alpha) { b->alpha = alpha; return 0; }
+
+int afe_batch_set_preemphasis(afe_batch *b, float coefficient)
+{
+    return guarded([&] {
+        if (!(coefficient >= 0.f && coefficient < 1.f)) throw Error("pre-emphasis coefficient must be in [0, 1)");
+        b->eng->pre = coefficient;
+    });
+}
 
 int afe_batch_set_options(afe_batch *b, int stats_scope, int flags)
 {
     return guarded([&] {
         if (stats_scope < AFE_STATS_REFERENCE_BLOCK || stats_scope > AFE_STATS_CORPUS) throw Error("invalid stats scope");
-        if (b->d_tiles && ((stats_scope == AFE_STATS_CORPUS) != (b->scope == AFE_STATS_CORPUS)))
-            throw Error("set the statistics scope before afe_batch_plan");
-        b->scope = stats_scope; b->flags = flags;
+        // the per-group row counts, the group table and the corpus Normalizer are laid down by afe_batch_plan from the scope
+        if (b->d_tiles && stats_scope != b->scope) throw Error("set the statistics scope before afe_batch_plan");
+        b->scope = stats_scope; b->flags = flags; // every flag is read at run time
     });
 }
 
 int afe_batch_set_stream(afe_batch *b, void *cuda_stream)
 {
     b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    if (b->cnorm) b->cnorm->st = b->stream;
     return 0;
 }
 
@@ -542,35 +590,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         if (n_utts < 1) throw Error("plan: no utterances");
         DeviceGuard g(b->device);
         b->free_plan();
-        // tile geometry. Generic kernel (2 CTAs per SM): the cepstra tile holds up to 512 frames (<= 27 KB of shared memory).
-        // Warp-specialised kernel (1 CTA per SM): the tile takes what is left of the 227 KB, so that a whole utterance
-        // (<= ~600 frames with 3 magnitude buffers, <= ~1250 with 2, at 13 columns) is ONE tile: no halo, and the
-        // utterance is normalised before its rows are written.
-        const char *env_tc = getenv("AFE_TILE_FRAMES");
-        int tc = env_tc ? atoi(env_tc) : 512;
-        b->ws_planned = false;
-        if (b->ws_eligible()) {
-            int t_max = 0;
-            for (int u = 0; u < n_utts; u++)
-                t_max = std::max<int64_t>(t_max, std::min<int64_t>(std::max<int64_t>(0, (len[u] - (d.W - d.S)) / d.S), 1 << 30));
-            auto base = [&](int nbuf) { return d.N2 == 512 ? ws_smem_layout<512>(d.S, d.cols, 0, nbuf).total : ws_smem_layout<256>(d.S, d.cols, 0, nbuf).total; };
-            auto cap = [&](int nbuf) { return (227 * 1024 - base(nbuf)) / (d.cols * 4) / kRoundFrames * kRoundFrames; };
-            const int need = (t_max + kRoundFrames - 1) / kRoundFrames * kRoundFrames;
-            const int min_tc = kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1);
-            int nbuf = need <= cap(3) ? 3 : 2;
-            int tcw = std::min(std::max(need, min_tc), cap(nbuf));
-            if (env_tc) tcw = std::min(tcw, std::max(atoi(env_tc), min_tc));
-            if (tcw >= min_tc) {
-                b->ws_planned = true;
-                tc = tcw;
-                b->Lws = d.N2 == 512 ? ws_smem_layout<512>(d.S, d.cols, tc, nbuf) : ws_smem_layout<256>(d.S, d.cols, tc, nbuf);
-            }
-        }
-        if (!b->ws_planned) {
-            tc = std::min(tc, (6912 / d.cols) / kRoundFrames * kRoundFrames); // cepstra tile <= 27 KB: still 2 CTAs per SM
-            tc = std::max(tc, kRoundFrames * ((2 * d.D + 1 + kRoundFrames - 1) / kRoundFrames + 1));
-        }
-        b->tc_max = tc; b->nout_max = tc - 2 * d.D;
+        const FusedEngine &eng = *b->eng;
         b->n_utts = n_utts;
         b->sample_off.assign(off, off + n_utts);
         b->sample_len.assign(len, len + n_utts);
@@ -595,30 +615,10 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             const int T = std::min(afe_estimated_window_count((int)n, d.W, d.S), (int)std::max<int64_t>(0, (n - (d.W - d.S)) / d.S));
             if (T <= 2 * d.D || T < 1) throw Error("Can't process data, window count is too small"); // segmentercpu.cpp:65-66
             b->frame_off[u + 1] = b->frame_off[u] + T;
-            // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
-            int ntile = (T + b->nout_max - 1) / b->nout_max, best_cost = 1 << 30;
-            const bool whole = b->ws_planned && T <= b->tc_max; // k_fused_ws: a whole utterance in one tile needs no halo
-            if (whole) ntile = 1;
-            for (int cand = ntile; cand <= ntile + 3 && !whole; cand++) {
-                const int no = (T + cand - 1) / cand;
-                int cost = 0;
-                for (int t0 = 0; t0 < T; t0 += no) {
-                    const int c0 = std::max(0, t0 - d.D), c1 = std::min(T, t0 + std::min(no, T - t0) + d.D);
-                    cost += (c1 - c0 + kRoundFrames - 1) / kRoundFrames;
-                }
-                if (cost < best_cost) { best_cost = cost; ntile = cand; }
-            }
-            const int nout = (T + ntile - 1) / ntile;
             b->h_tile_begin[u] = (int)tiles.size();
-            b->max_tiles_per_utt = std::max(b->max_tiles_per_utt, ntile);
             if (!corpus) tile_begin.push_back((int)tiles.size());
-            for (int t0 = 0; t0 < T; t0 += nout) {
-                Tile tl;
-                tl.pcm_off = off[u]; tl.out_row0 = b->frame_off[u]; tl.T = T; tl.t0 = t0;
-                tl.nout = std::min(nout, T - t0); tl.group = corpus ? 0 : u;
-                tl.tile0 = b->h_tile_begin[u]; tl.ntiles = (T + nout - 1) / nout;
-                tiles.push_back(tl);
-            }
+            const int ntile = eng.plan_rows(tiles, off[u], b->frame_off[u], T, 0, T, corpus ? 0 : u);
+            b->max_tiles_per_utt = std::max(b->max_tiles_per_utt, ntile);
             const double cnt = !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
             if (corpus) corpus_count += cnt; else counts.push_back(cnt);
         }
@@ -628,13 +628,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         b->aligned = aligned;
         b->n_tiles = (int)tiles.size();
         b->n_groups = corpus ? 1 : n_utts;
-        if (b->ws_planned) {
-            if (b->Lws.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
-        } else {
-            b->L = d.N2 == 512 ? layout_for<512>(b) : layout_for<256>(b);
-            if (b->L.total > 227 * 1024) throw Error("fused kernel shared-memory budget exceeded");
-        }
-        AFE_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, b->device));
+        b->corpus_blocks = 2 * eng.sm_count;
         AFE_CUDA(cudaMalloc(&b->d_tiles, sizeof(Tile) * tiles.size()));
         AFE_CUDA(cudaMemcpy(b->d_tiles, tiles.data(), sizeof(Tile) * tiles.size(), cudaMemcpyHostToDevice));
         if (d.p.norm != AFE_NORM_NONE) {
@@ -644,15 +638,22 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             AFE_CUDA(cudaMalloc(&b->d_counts, sizeof(double) * counts.size()));
             AFE_CUDA(cudaMemcpy(b->d_counts, counts.data(), sizeof(double) * counts.size(), cudaMemcpyHostToDevice));
             AFE_CUDA(cudaMalloc(&b->d_partials, sizeof(double) * 4 * w * tiles.size()));
-            AFE_CUDA(cudaMalloc(&b->d_stats, sizeof(double) * (4 * w + 1) * b->n_groups));
             if (corpus) {
-                const int sb[2] = {0, kCorpusBlocks};
-                AFE_CUDA(cudaMalloc(&b->d_scratch, sizeof(double) * 4 * w * kCorpusBlocks));
+                // the corpus record lives in a Normalizer of dim = width (all three streams in one record)
+                if (afe_normalizer_create(d.p.norm, d.width, b->device, &b->cnorm) != 0) throw Error(afe_last_error());
+                b->cnorm->st = b->stream;
+                b->d_stats = b->cnorm->ns.rec.p;
+                const int sb[2] = {0, b->corpus_blocks};
+                AFE_CUDA(cudaMalloc(&b->d_scratch, sizeof(double) * 4 * w * b->corpus_blocks));
                 AFE_CUDA(cudaMalloc(&b->d_scratch_begin, sizeof(sb)));
                 AFE_CUDA(cudaMemcpy(b->d_scratch_begin, sb, sizeof(sb), cudaMemcpyHostToDevice));
-            }
-            AFE_CUDA(cudaMalloc(&b->d_counters, sizeof(int) * b->n_groups));
-            AFE_CUDA(cudaMemset(b->d_counters, 0, sizeof(int) * b->n_groups));
+            } else
+                AFE_CUDA(cudaMalloc(&b->d_stats, sizeof(double) * (4 * w + 1) * b->n_groups));
+            AFE_CUDA(cudaMalloc(&b->d_counters, sizeof(int) * (b->n_groups + 1)));
+            AFE_CUDA(cudaMemset(b->d_counters, 0, sizeof(int) * (b->n_groups + 1)));
+            AFE_CUDA(cudaMalloc(&b->d_flags, sizeof(unsigned) * b->n_groups));
+            AFE_CUDA(cudaMemset(b->d_flags, 0, sizeof(unsigned) * b->n_groups));
+            b->epoch = 0;
             AFE_CUDA(cudaMalloc(&b->d_mean, sizeof(float) * w * b->n_groups));
             AFE_CUDA(cudaMalloc(&b->d_scale, sizeof(float) * w * b->n_groups));
         }
@@ -667,7 +668,8 @@ int afe_batch_frame_offsets(const afe_batch *b, int64_t *fo)
 }
 int afe_batch_num_tiles(const afe_batch *b) { return b->n_tiles; }
 int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
-const char *afe_batch_kernel_name(const afe_batch *b) { return b->use_ws() ? "k_fused_ws" : "k_fused_mfcc"; }
+const char *afe_batch_kernel_name(const afe_batch *) { return "k_fused_mfcc"; }
+afe_normalizer *afe_batch_normalizer(afe_batch *b) { return b->cnorm; }
 
 int afe_batch_extract_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
 {
@@ -682,7 +684,7 @@ int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out)
             throw Error("corpus statistics need the two-pass sequence: extract_device, corpus_stats, allreduce, normalize_device");
         b->last_launches = 0;
         const bool fuse = b->fuse_norm();
-        run_extract(b, d_pcm, d_out, 0, -1, fuse);   // per-utterance scopes: the last tile of an utterance normalises it
+        run_extract(b, d_pcm, d_out, 0, -1, fuse);   // per-utterance scopes: normalised inside the one launch
         if (b->d.p.norm != AFE_NORM_NONE && !fuse) { run_reduce(b); run_normalize(b, d_out); }
     });
 }
@@ -698,21 +700,11 @@ int afe_batch_corpus_stats(afe_batch *b, double **d_stats, int *stats_len)
     });
 }
 
-int afe_normalizer_allreduce(afe_batch *b, void *comm)
-{
-    return guarded([&] {
-        DeviceGuard g(b->device);
-        if (b->scope != AFE_STATS_CORPUS) throw Error("allreduce: statistics scope is not CORPUS");
-        const int w = b->d.width;
-        // one fused group: sums + count (ncclSum), minima (ncclMin), maxima (ncclMax) — 4w+1 doubles, latency bound
-        nccl_allreduce_stats(comm, b->d_stats, 2 * w + 1, b->d_stats + 2 * w + 1, w, b->d_stats + 3 * w + 1, w, b->stream);
-    });
-}
-
 int afe_batch_set_corpus_stats(afe_batch *b, const double *h_stats, int stats_len)
 {
     return guarded([&] {
         DeviceGuard g(b->device);
+        if (b->d.p.norm == AFE_NORM_NONE) throw Error("set_corpus_stats: norm is NONE");
         if (stats_len != (4 * b->d.width + 1) * b->n_groups) throw Error("set_corpus_stats: wrong length");
         AFE_CUDA(cudaMemcpyAsync(b->d_stats, h_stats, sizeof(double) * stats_len, cudaMemcpyHostToDevice, b->stream));
         AFE_CUDA(cudaStreamSynchronize(b->stream));
@@ -733,8 +725,8 @@ int afe_batch_synchronize(afe_batch *b)
     return guarded([&] { DeviceGuard g(b->device); AFE_CUDA(cudaStreamSynchronize(b->stream)); });
 }
 
-// End-to-end with host buffers. h_pcm / h_out should be pinned for full PCIe speed (pageable memory works too).
-// The shard is cut into up to 32 utterance chunks and pipelined over three streams: H2D of chunk c+1, the kernels of
+// End to end with host buffers. h_pcm / h_out should be pinned for full PCIe speed (pageable memory works too).
+// The shard is cut into utterance chunks and pipelined over three streams: H2D of chunk c+1, the kernels of
 // chunk c and D2H of chunk c-1 overlap (PCIe is full duplex), so the call is bound by max(H2D, D2H) instead of their sum.
 int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
 {
@@ -771,7 +763,6 @@ int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out)
             b->ev_in.push_back(e1); b->ev_k.push_back(e2);
         }
         b->last_launches = 0;
-        if (b->mc_alpha != b->alpha) { build_mel_const(d, b->alpha, b->mc); b->mc_alpha = b->alpha; }
         const bool norm = d.p.norm != AFE_NORM_NONE;
         for (int c = 0; c < n_chunks; c++) {
             const int u0 = (int)((int64_t)b->n_utts * c / n_chunks), u1 = (int)((int64_t)b->n_utts * (c + 1) / n_chunks);

@@ -168,21 +168,40 @@ template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
 //              power-of-two factor 0.5/N2 into its mel weights)
 template <int N2, int NZ, bool FAST, bool SCALED = true>
 __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneConsts<N2, NZ> &lc, float2 *scratch,
-                                              float *mag_out, int lf)
+                                              float *mag_out, int lf, float pre = 0.f)
 {
     using C = FftCfg<N2>;
     constexpr int M = C::M, R = C::R, RS = C::RS;
     float2 x[16];
+    if (pre == 0.f) { // warp-uniform: the reference has no pre-emphasis (segmentercpu.cpp:21-27), this is its path
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-        if (n1 < NZ) {
-            const uint32_t w = words[R * n1 + lf];
-            const float2 wn = lc.win[n1];
-            const float lo = (float)(int)(short)(w & 0xffffu);
-            const float hi = (float)((int)w >> 16);
-            x[n1] = __fmul2_rn(make_float2(lo, hi), wn);
-        } else
-            x[n1] = make_float2(0.f, 0.f);
+        for (int n1 = 0; n1 < 16; n1++) {
+            if (n1 < NZ) {
+                const uint32_t w = words[R * n1 + lf];
+                const float2 wn = lc.win[n1];
+                const float lo = (float)(int)(short)(w & 0xffffu);
+                const float hi = (float)((int)w >> 16);
+                x[n1] = __fmul2_rn(make_float2(lo, hi), wn);
+            } else
+                x[n1] = make_float2(0.f, 0.f);
+        }
+    } else {
+        // per-frame pre-emphasis y[j] = x[j] - pre * x[j-1], y[0] = (1 - pre) * x[0] (HTK / Kaldi convention), then the
+        // window: w[j] * x[j] + (-pre * w[j]) * x[j-1]
+        const float2 mp = make_float2(-pre, -pre);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; n1++) {
+            if (n1 < NZ) {
+                const int idx = R * n1 + lf;
+                const uint32_t w = words[idx], wp = words[idx > 0 ? idx - 1 : 0];
+                const float2 wn = lc.win[n1];
+                const float lo = (float)(int)(short)(w & 0xffffu);
+                const float hi = (float)((int)w >> 16);
+                const float prev = idx > 0 ? (float)((int)wp >> 16) : lo;
+                x[n1] = __ffma2_rn(make_float2(prev, lo), __fmul2_rn(wn, mp), __fmul2_rn(make_float2(lo, hi), wn));
+            } else
+                x[n1] = make_float2(0.f, 0.f);
+        }
     }
     fft16_in<NZ>(x);
     // twiddle + exchange: S[k1][n2]

@@ -21,7 +21,8 @@
 //            delta rows through shared memory, then coalesced row writes.
 //   norm     the last tile of an utterance to finish reduces the records and normalises the utterance in place (L2).
 // Two CTA barriers per 32 frames (v1 serialised phase 2 on one warp and lost 39 % of its issue slots at the barrier,
-// profiles/r01_v1_k_fused_summary.txt). The warp-specialised alternative is afe_fused_ws.cuh.
+// profiles/r01_v1_k_fused_summary.txt). A warp-specialised persistent variant was measured 1.6 % slower in round 1
+// (profiles/r01_ws_vs_generic.txt) and removed.
 // Replaces, for whole utterances: segmenter.cl, AppleFFT fft0, mfcc.cl kernelTranspose+kernelFilter, DCT.cl,
 // delta.cl and norm.cl:kernelSum.
 #pragma once
@@ -73,11 +74,27 @@ struct FusedArgs {
                          // statistics records through distributed shared memory and write normalised rows directly
     int tile_base;       // absolute index of this launch's first tile
     int norm_type, norm_after_dyn;
-    int debug_skip;      // timing experiments only (AFE_DEBUG_SKIP): 1 skip FFT calls, 2 skip mel/DCT, 4 skip phase 3 + normalise
+#ifdef AFE_DEVTOOLS
+    int debug_skip;      // timing experiments only (tools build, -DAFE_DEVTOOLS): 1 skip FFT calls, 2 skip mel/DCT, 4 skip phase 3
+#endif
     int W, S, nb, dct_len, cols, width, l1, l2, nstreams;
-    int q1;              // reproduce the single-block flush quirk
+    int q1;              // 1: reproduce the single-block flush quirk Q1 for the last D rows of an utterance; 2: for EVERY row of
+                         // the tile (the streaming object's flush block after a single set_input, mfcccpu.cpp:439)
     int use_tma;
-    int stats_rows_mode; // 0: no stats, 1: rows < T-D, 2: all rows
+    int stats_rows_mode; // 0: no stats, 1: rows < T-D, 2: all rows of the utterance, 3: the output rows of the group's tiles
+                         // (a block of the streaming object: stats_count rows, normalizercpu.cpp:22-30)
+    int stats_count;     // mode 3: rows of the whole group
+    int use_last;        // 1: no statistics; normalise with g_mean / g_scale of the tile's group (use_last_stats, mfcccpu.cpp:389)
+    float *g_mean, *g_scale; // [groups][width] finalised mean / scale: exported by whoever finalises a group (when non-null),
+                         // read by use_last tiles and by the normaliser roles of the long-utterance scheme
+    // long utterances (more than 8 tiles): the launch carries 2 * ntiles_launch CTAs that take their role from a ticket:
+    // the first ntiles_launch tickets extract a tile each, the others wait for their tile's group to be finalised
+    // (flags[group] == epoch, set by the group's last tile) and normalise that tile's rows in place through L2
+    int *work_counter;   // self-resetting ticket counter, or nullptr
+    unsigned *flags;     // [groups]
+    unsigned epoch;
+    int ntiles_launch;
+    float pre;           // pre-emphasis coefficient applied per frame before the window (0: none, the reference's behaviour)
     int stats_kind;      // 0: none, 1: sums (CMN), 2: + sums of squares (CVN), 3: + min/max (MINMAX)
     int tc_max;          // capacity (frames) of the cepstra tile
     float rden1, rden2;  // 1 / (2*sum(l^2))
@@ -259,7 +276,7 @@ __device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, co
     const int cols = a.cols, width = a.width, T = tl.T, t0 = tl.t0, nout = tl.nout;
     const int rp = nthreads / cols, g = tid / cols, c = tid - g * cols;
     if (g >= rp) return;
-    const int rq = a.q1 ? max(0, T - 6 - t0) : nout; // first row written with the static of 6 rows earlier (Q1)
+    const int rq = a.q1 ? (a.q1 == 2 ? 0 : max(0, T - 6 - t0)) : nout; // first row written with the static of 6 rows earlier (Q1)
     const float rden1 = a.rden1, rden2 = a.rden2;
     double sum[3] = {0.0, 0.0, 0.0}, sumsq[3] = {0.0, 0.0, 0.0};
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -323,12 +340,75 @@ __device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, co
 
 } // namespace dev
 
+namespace dev {
+// In-place (x - mean) [* scale] over one tile's rows, 128-bit accesses on the 16-byte aligned body of the tile's contiguous
+// region; columns tracked incrementally (no division in the loop). Used by K3 (k_normalize_tiles) and by the normaliser
+// roles of the long-utterance scheme, so both give the same bits. s_ms: 2 * width floats of shared memory.
+__device__ __forceinline__ void normalise_tile_rows(float *__restrict__ out, const Tile &tl, int width, int norm_type,
+                                                    const float *__restrict__ mean, const float *__restrict__ scale, float *s_ms)
+{
+    float *base = out + (tl.out_row0 + tl.t0) * (long long)width;
+    const int n = tl.nout * width;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        s_ms[i] = __ldcg(mean + (long long)tl.group * width + i);
+        s_ms[width + i] = norm_type == AFE_NORM_CMN ? 1.f : __ldcg(scale + (long long)tl.group * width + i);
+    }
+    __syncthreads();
+    const float *m = s_ms, *sc = s_ms + width;
+    const bool cmn = norm_type == AFE_NORM_CMN;
+    const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) >> 2));
+    const int n4 = (n - head) >> 2, tail0 = head + 4 * n4;
+    if ((int)threadIdx.x < head) {
+        const int i = threadIdx.x;
+        const float v = __ldcg(base + i) - m[i % width];
+        base[i] = cmn ? v : v * sc[i % width];
+    }
+    if ((int)threadIdx.x < n - tail0) {
+        const int i = tail0 + threadIdx.x, c = i % width;
+        const float v = __ldcg(base + i) - m[c];
+        base[i] = cmn ? v : v * sc[c];
+    }
+    float4 *p4 = reinterpret_cast<float4 *>(base + head);
+    int c = (head + 4 * (int)threadIdx.x) % width;
+    const int cstep = (4 * (int)blockDim.x) % width;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+        float4 v = __ldcg(p4 + j);
+        int c1 = c + 1; if (c1 >= width) c1 -= width;
+        int c2 = c1 + 1; if (c2 >= width) c2 -= width;
+        int c3 = c2 + 1; if (c3 >= width) c3 -= width;
+        v.x -= m[c]; v.y -= m[c1]; v.z -= m[c2]; v.w -= m[c3];
+        if (!cmn) { v.x *= sc[c]; v.y *= sc[c1]; v.z *= sc[c2]; v.w *= sc[c3]; }
+        p4[j] = v;
+        c += cstep; if (c >= width) c -= width;
+    }
+}
+
+// Normaliser role of the long-utterance scheme: wait (bounded) until the tile's group is finalised, then normalise the tile.
+__device__ __forceinline__ void normalise_role(const FusedArgs &a, const Tile tl, float *s_ms)
+{
+    if (threadIdx.x == 0) {
+        // The flag is set by the group's last extracting CTA, which holds an earlier ticket and is therefore running or
+        // done: the wait always ends. Bounded all the same (a lost flag must trap, never hang the GPU).
+        unsigned v = 0;
+        for (unsigned spin = 0; spin < (1u << 26); spin++) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags + tl.group) : "memory");
+            if (v == a.epoch) break;
+            __nanosleep(128);
+        }
+        if (v != a.epoch) __trap();
+    }
+    __syncthreads();
+    normalise_tile_rows(a.out, tl, a.width, a.norm_type, a.g_mean, a.g_scale, s_ms);
+}
+} // namespace dev
+
 // KF = filters per warp in phase 2 (ceil(num_banks / WARPS), rounded up to 3, 5 or 8): the phase is unrolled KF times,
 // so a tight bound keeps the round loop inside the instruction cache.
-template <int N2, int NZ, bool FAST, int kFusedWarps, int KF>
+template <int N2, int NZ, int kFusedWarps, int KF>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
+    constexpr bool FAST = false; // MUFU log approximation: measured in round 1, not shipped
     using C = dev::FftCfg<N2>;
     constexpr int kFusedThreads = 32 * kFusedWarps, kWarpFrames = kRoundFrames / kFusedWarps;
     constexpr int R = C::R, FPW = C::FPW, SCR = C::SCR;
@@ -345,7 +425,22 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     unsigned char *w_pcm = wbase + L.w_pcm;
     float2 *w_scratch = reinterpret_cast<float2 *>(smem + L.off_part + warp * L.w_scratch); // aliased by s_part in phase 2
 
-    const int tile_idx = a.tile_base + blockIdx.x;
+    int tile_local = blockIdx.x;
+    if (a.work_counter) { // long-utterance scheme: roles by ticket, so that a waiting CTA can only wait for RUNNING ones
+        __shared__ int s_role;
+        if (tid == 0) {
+            const int t = atomicAdd(a.work_counter, 1);
+            if (t == 2 * a.ntiles_launch - 1) *a.work_counter = 0; // every ticket of this launch is out: ready for the next
+            s_role = t;
+        }
+        __syncthreads();
+        tile_local = s_role;
+        if (tile_local >= a.ntiles_launch) {
+            dev::normalise_role(a, a.tiles[a.tile_base + tile_local - a.ntiles_launch], reinterpret_cast<float *>(smem));
+            return;
+        }
+    }
+    const int tile_idx = a.tile_base + tile_local;
     const Tile tl = a.tiles[tile_idx];
     const int D = a.l1 + a.l2, cols = a.cols;
     const int c0f = max(0, tl.t0 - D), c1f = min(tl.T, tl.t0 + tl.nout + D);
@@ -403,11 +498,14 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             }
 #pragma unroll
             for (int it = 0; it < kWarpFrames / FPW; it++) {
-                if (it * FPW >= nfw || (a.debug_skip & 1)) break;
+                if (it * FPW >= nfw) break;
+#ifdef AFE_DEVTOOLS
+                if (a.debug_skip & 1) break;
+#endif
                 const int fl = it * FPW + fw;                    // frame within the warp's 8 (adjacent frames per call)
                 const int fr = warp * kWarpFrames + fl;          // frame within the round
                 const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
-                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + mag_row(fr) * kMagStride, lf);
+                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + mag_row(fr) * kMagStride, lf, a.pre);
             }
             // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
             if (a.use_tma && lane == 0 && r + 1 < nrounds) issue_tma(r + 1);
@@ -417,7 +515,11 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         // ---- phase 2: lane = frame of the round, warp = filter class (filters warp, warp + WARPS, ...).
         //      Three unrolled passes over the warp's <= KF filters - sums, logs, DCT - so that the independent filters'
         //      long dependency chains (accumulation, logf) interleave instead of running back to back.
+        #ifdef AFE_DEVTOOLS
         if (lane < nfr && !(a.debug_skip & 2)) {
+#else
+        if (lane < nfr) {
+#endif
             float es[KF];
             int woff = mc.wstart[warp]; // running float4 offset into this warp class's weight lists (uniform)
             // the first 8-bin chunk of every filter of this warp is loaded up front (2*KF independent 128-bit loads in
@@ -523,20 +625,28 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     float *s_dd = reinterpret_cast<float *>(smem + L.off_dd);
     double *s_red = reinterpret_cast<double *>(smem + L.off_red);
     const int T = tl.T, t0 = tl.t0, nout = tl.nout, l1 = a.l1, l2 = a.l2;
+#ifdef AFE_DEVTOOLS
     if (a.debug_skip & 4) return;
+#endif
     // ownership of the generic row writer and of the fused normalisation: thread = (row group r_off, output column col)
     const int width = a.width;
     const int rpp = kFusedThreads / width; // rows per pass (width <= 128 enforced by the host)
     const bool active = tid < rpp * width;
     const int r_off = tid / width, col = tid - r_off * width;
     const int strm = col / cols, c = col - strm * cols;
-    const int n_stats = a.stats_rows_mode == 1 ? T - D : (a.stats_rows_mode == 2 ? T : 0);
+    const int n_stats = a.stats_rows_mode == 1 ? T - D : a.stats_rows_mode == 2 ? T : a.stats_rows_mode == 3 ? a.stats_count : 0;
     // source of this thread's column: src[r * cols]; statics of the Q1 rows come from D rows earlier
     const float *src = strm == 0 ? s_cep + (t0 - c0f) * cols + c : strm == 1 ? s_dhat + l2 * cols + c : s_dd + c;
-    const int rq = (a.q1 && strm == 0) ? max(0, T - D - t0) : nout; // first row written with the shifted static
-    const int rs = min(nout, max(0, n_stats - t0));                 // rows [0, rs) enter the statistics
+    const int rq = (a.q1 && strm == 0) ? (a.q1 == 2 ? 0 : max(0, T - D - t0)) : nout; // first row written with the shifted static
+    const int rs = a.stats_rows_mode == 3 ? nout : min(nout, max(0, n_stats - t0)); // rows [0, rs) enter the statistics
     const bool fast3 = a.nstreams == 3 && l1 == 3 && l2 == 3;
-    if (fast3 && a.cluster_norm) {
+    if (fast3 && a.use_last) {
+        // flush block of the streaming object: the previous block's statistics (mfcccpu.cpp:389), rows written normalised
+        const int cc = tid % cols;
+        const float *gm = a.g_mean + (long long)tl.group * width, *gs = a.g_scale + (long long)tl.group * width;
+        const float norm3[6] = {gm[cc], gm[cols + cc], gm[2 * cols + cc], gs[cc], gs[cols + cc], gs[2 * cols + cc]};
+        dev::phase3_l3<2>(0, a, tl, s_cep, c0f, c1f, nullptr, tid, kFusedThreads, rs, norm3);
+    } else if (fast3 && a.cluster_norm) {
         // One cluster = the tiles of one utterance (cluster rank = tile number). Statistics first (MODE 1), records
         // exchanged through distributed shared memory and summed in tile order - the order of the ticket scheme below and
         // of K2, so the results are bitwise the same -, then every tile writes its rows already normalised (MODE 2):
@@ -572,6 +682,10 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             else if (a.norm_type == AFE_NORM_MINMAX) sc = 1.f / fmaxf(fabsf((float)lo - m), fabsf((float)hi - m));
             if (!a.norm_after_dyn && tid >= cols) m = 0.f;
             s_mean[tid] = m; s_scale[tid] = sc;
+            if (a.g_mean && tile_idx == tl.tile0) { // every tile holds the same values: the group's first tile exports them
+                a.g_mean[(long long)tl.group * width + tid] = m;
+                a.g_scale[(long long)tl.group * width + tid] = sc;
+            }
         }
         __syncthreads();
         {
@@ -693,24 +807,37 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 else if (a.norm_type == AFE_NORM_MINMAX) sc = 1.f / fmaxf(fabsf((float)lo - m), fabsf((float)hi - m));
                 if (!a.norm_after_dyn && tid >= cols) m = 0.f;
                 s_mean[tid] = m; s_scale[tid] = sc;
+                if (a.g_mean) {
+                    a.g_mean[(long long)tl.group * width + tid] = m;
+                    a.g_scale[(long long)tl.group * width + tid] = sc;
+                }
+            }
+            if (a.work_counter) {
+                // long utterance: the normaliser roles take it from here (one per tile, all SMs) instead of this one CTA
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + tl.group), "r"(a.epoch) : "memory");
+                return;
             }
             __syncthreads();
             if (active) { // same (row group, column) ownership as the row writer: no division in the loop
-                float *o = a.out + tl.out_row0 * (long long)width + col;
+                // rows of the group = first tile's t0 .. last tile's end (the whole utterance, or a block of a stream)
+                const int rb = a.tiles[tl.tile0].t0, re = a.tiles[tl.tile0 + tl.ntiles - 1].t0 + a.tiles[tl.tile0 + tl.ntiles - 1].nout;
+                float *o = a.out + (tl.out_row0 + rb) * (long long)width + col;
                 const float m = s_mean[col], sc = a.norm_type == AFE_NORM_CMN ? 1.f : s_scale[col];
                 const bool cmn = a.norm_type == AFE_NORM_CMN;
                 const int step = rpp * width;
                 o += r_off * width;
-                int r = r_off;
+                int r = rb + r_off;
                 constexpr int U = 8; // loads in flight per thread: the rows come from L2, ~300 cycles away
-                for (; r + (U - 1) * rpp < T; r += U * rpp, o += U * step) {
+                for (; r + (U - 1) * rpp < re; r += U * rpp, o += U * step) {
                     float v[U];
 #pragma unroll
                     for (int k = 0; k < U; k++) v[k] = __ldcg(o + k * step);
 #pragma unroll
                     for (int k = 0; k < U; k++) o[k * step] = cmn ? v[k] - m : (v[k] - m) * sc;
                 }
-                for (; r < T; r += rpp, o += step) *o = cmn ? __ldcg(o) - m : (__ldcg(o) - m) * sc;
+                for (; r < re; r += rpp, o += step) *o = cmn ? __ldcg(o) - m : (__ldcg(o) - m) * sc;
             }
         }
     }

@@ -88,10 +88,10 @@ void upload_window(const Derived &d, const float *window, MelTables &t, cudaStre
 
 // segment + window into float frames [frames][N2] (SegmenterOpenCL::segment_data replacement)
 void launch_segment(const int16_t *d_pcm, const float *d_window, float *d_out, int frames, int W, int S, int N2,
-                    cudaStream_t st);
+                    cudaStream_t st, float pre = 0.f);
 // fused segment+window+FFT+|X|/N2 -> d_mag [frames][bins]
 void launch_fft_mag(const Derived &d, const FftTables &ft, const MelTables &mt, const int16_t *d_pcm, float *d_mag,
-                    int frames, cudaStream_t st);
+                    int frames, cudaStream_t st, float pre = 0.f);
 // mel+log (+DCT) : d_mag [frames][bins] -> d_mel [frames][nb], d_cep [frames][dct_len]
 void launch_mel_dct(const Derived &d, const MelTables &mt, const float *d_mag, float *d_mel, float *d_cep, int frames,
                     cudaStream_t st);
@@ -103,11 +103,52 @@ void launch_delta(const float *d_in, float *d_out, int rows, int dim, int L, cud
 void launch_colstats(const float *d_x, int rows, int dim, int norm_type, float *d_mean, float *d_scale, cudaStream_t st);
 void launch_affine(float *d_x, int rows, int dim, int norm_type, const float *d_mean, const float *d_scale,
                    cudaStream_t st);
+// running record (sum | sumsq | count | min | max) of a Normalizer: clear, add the rows' column statistics, finalise
+void launch_record_reset(double *d_rec, int dim, cudaStream_t st);
+void launch_record_accumulate(const float *d_x, int rows, int dim, double *d_rec, cudaStream_t st);
+void launch_record_finalize(const double *d_rec, int dim, int norm_type, float *d_mean, float *d_scale, cudaStream_t st);
 // interleave [static | delta | acc] rows into d_out [rows][width]
 void launch_pack(const float *d_s, const float *d_d1, const float *d_d2, float *d_out, int rows, int cols, int nstreams,
                  cudaStream_t st);
 
 int kernel_launch_count();      // monotonically increasing count of kernel launches by this library
 void count_launch(int n = 1);
+int sm_count_of(int device);    // cudaDevAttrMultiProcessorCount, cached per device
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        AFE_CUDA(cudaMalloc(&p, sizeof(T) * (count > 0 ? count : 1)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+// ---- Normalizer state (NormalizerCPU / NormalizerOpenCL, normalizercpu.h:7-9): last statistics + a running record.
+// record layout (the one all-reduced across ranks): sum[dim] | sumsq[dim] | count | min[dim] | max[dim], doubles
+struct NormState {
+    int type = AFE_NORM_NONE, dim = 0;
+    DevBuf<float> mean, scale;
+    DevBuf<double> rec;         // running statistics record, 4*dim+1
+    void init(int t, int d);
+    int rec_len() const { return 4 * dim + 1; }
+    // NormalizerCPU::normalize (normalizercpu.cpp:22-89): block statistics (unless use_last) + affine, in place
+    void normalize(float *d_x, int rows, bool use_last, cudaStream_t st);
+    void reset_record(cudaStream_t st);
+    void accumulate(const float *d_x, int rows, cudaStream_t st);   // record += column statistics of the rows
+    void finalize(cudaStream_t st);                                  // record -> mean / scale (normalizercpu.cpp:31-66)
+    void apply(float *d_x, int rows, cudaStream_t st);              // (x - mean) [* scale]
+};
 
 } // namespace afe
+
+// ---- the C-ABI Normalizer object (afe_stream.cu); afe_batch routes its corpus statistics through one of these
+struct afe_normalizer {
+    int device = 0;
+    cudaStream_t own_st = nullptr, st = nullptr; // st: the stream in use (own, or the owning batch's)
+    afe::NormState ns;
+};

@@ -68,10 +68,17 @@ void nccl_allreduce_stats(void *comm, double *d_sums, int n_sum, double *d_mins,
     if (!comm) throw Error("allreduce: null communicator");
     const int kF64 = 8, kSum = 0, kMax = 2, kMin = 3;
     check(a.group_start(), "ncclGroupStart");
-    check(a.all_reduce(d_sums, d_sums, (size_t)n_sum, kF64, kSum, comm, st), "ncclAllReduce(sum)");
-    check(a.all_reduce(d_mins, d_mins, (size_t)n_min, kF64, kMin, comm, st), "ncclAllReduce(min)");
-    check(a.all_reduce(d_maxs, d_maxs, (size_t)n_max, kF64, kMax, comm, st), "ncclAllReduce(max)");
-    check(a.group_end(), "ncclGroupEnd");
+    // Record the first failure but ALWAYS close the group: an exception between GroupStart and GroupEnd would leave it
+    // open on this thread and the next collective (ours or torch's, same libnccl) would hang.
+    int rc = 0;
+    const char *what = nullptr;
+    auto step = [&](int r, const char *w) { if (r != 0 && rc == 0) { rc = r; what = w; } };
+    step(a.all_reduce(d_sums, d_sums, (size_t)n_sum, kF64, kSum, comm, st), "ncclAllReduce(sum)");
+    if (rc == 0) step(a.all_reduce(d_mins, d_mins, (size_t)n_min, kF64, kMin, comm, st), "ncclAllReduce(min)");
+    if (rc == 0) step(a.all_reduce(d_maxs, d_maxs, (size_t)n_max, kF64, kMax, comm, st), "ncclAllReduce(max)");
+    const int rc_end = a.group_end();
+    if (rc != 0) check(rc, what);
+    check(rc_end, "ncclGroupEnd");
 }
 } // namespace afe
 

@@ -3,6 +3,7 @@
 // CPU classes' numerics. The throughput path is the fused kernel in afe_fused.cuh; these serve the block-wise
 // ParamBase API where a block is small and the spectrum must persist across apply() calls (VTLN sweeps).
 #include <cfloat>
+#include <mutex>
 
 #include "afe_internal.h"
 #include "afe_fft.cuh"
@@ -10,24 +11,50 @@
 
 namespace afe {
 
+int sm_count_of(int device)
+{
+    static std::mutex mu;
+    static int cache[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= 64) device = 0;
+    if (!cache[device]) AFE_CUDA(cudaDeviceGetAttribute(&cache[device], cudaDevAttrMultiProcessorCount, device));
+    return cache[device];
+}
+// grid cap of the grid-stride stage kernels: `per_sm` CTAs per SM of the current device
+static int grid_cap(int per_sm)
+{
+    int dev = 0;
+    AFE_CUDA(cudaGetDevice(&dev));
+    return sm_count_of(dev) * per_sm;
+}
+
 // ------------------------------------------------------------------------------------------------ segmenter
 // out[N2*f + j] = window[j] * pcm[f*S + j] (j < W), 0 beyond   — segmentercpu.cpp:17-28 / segmenter.cl:1-22
+// pre != 0: per-frame pre-emphasis before the window, x[j] - pre * x[j-1] with x[-1] := x[0] (not in the reference)
+__device__ __forceinline__ float windowed_sample(const int16_t *__restrict__ frame, const float *__restrict__ window, int j, float pre)
+{
+    const float x = (float)frame[j];
+    if (pre == 0.f) return __fmul_rn(window[j], x);
+    const float xp = (float)frame[j > 0 ? j - 1 : 0];
+    return fmaf(xp, __fmul_rn(window[j], -pre), __fmul_rn(x, window[j]));
+}
+
 __global__ void k_segment(const int16_t *__restrict__ pcm, const float *__restrict__ window, float *__restrict__ out,
-                          int frames, int W, int S, int N2)
+                          int frames, int W, int S, int N2, float pre)
 {
     const long long n = (long long)frames * N2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int f = (int)(i / N2), j = (int)(i - (long long)f * N2);
-        out[i] = j < W ? __fmul_rn(window[j], (float)pcm[(long long)f * S + j]) : 0.f;
+        out[i] = j < W ? windowed_sample(pcm + (long long)f * S, window, j, pre) : 0.f;
     }
 }
 void launch_segment(const int16_t *d_pcm, const float *d_window, float *d_out, int frames, int W, int S, int N2,
-                    cudaStream_t st)
+                    cudaStream_t st, float pre)
 {
     if (frames <= 0) return;
     const long long n = (long long)frames * N2;
-    const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    k_segment<<<grid, 256, 0, st>>>(d_pcm, d_window, d_out, frames, W, S, N2);
+    const int grid = (int)std::min<long long>((n + 255) / 256, grid_cap(16));
+    k_segment<<<grid, 256, 0, st>>>(d_pcm, d_window, d_out, frames, W, S, N2, pre);
     AFE_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -36,7 +63,7 @@ void launch_segment(const int16_t *d_pcm, const float *d_window, float *d_out, i
 // Fast path (N2 = 256/512, even S): the same in-register FFT as the fused kernel, PCM read straight from global.
 template <int N2, int NZ>
 __global__ void __launch_bounds__(128) k_fft_mag(const int16_t *__restrict__ pcm, const float2 *window2, const float2 *tw_a,
-                                                 const float2 *tw_p, float *__restrict__ mag, int frames, int S)
+                                                 const float2 *tw_p, float *__restrict__ mag, int frames, int S, float pre)
 {
     using C = dev::FftCfg<N2>;
     __shared__ float2 scratch[4 * C::FPW * C::SCR];
@@ -52,19 +79,19 @@ __global__ void __launch_bounds__(128) k_fft_mag(const int16_t *__restrict__ pcm
         const int fc = act ? f : frames - 1;
         const uint32_t *words = reinterpret_cast<const uint32_t *>(pcm + (long long)fc * S);
         dev::fft_frame_mag<N2, NZ, false>(words, lc, scratch + (warp * C::FPW + fw) * C::SCR,
-                                          act ? mag + (long long)f * C::BINS : s_dump, lf);
+                                          act ? mag + (long long)f * C::BINS : s_dump, lf, pre);
     }
 }
 
 // Generic path: any power-of-two N2 <= 4096, any W/S. One CTA per frame, radix-2 Stockham in shared memory.
 __global__ void k_fft_mag_generic(const int16_t *__restrict__ pcm, const float *__restrict__ window,
-                                  float *__restrict__ mag, int frames, int W, int S, int N2)
+                                  float *__restrict__ mag, int frames, int W, int S, int N2, float pre)
 {
     extern __shared__ float2 sm[]; // 2 * N2
     float2 *a = sm, *b = sm + N2;
     for (int f = blockIdx.x; f < frames; f += gridDim.x) {
         for (int j = threadIdx.x; j < N2; j += blockDim.x)
-            a[j] = make_float2(j < W ? __fmul_rn(window[j], (float)pcm[(long long)f * S + j]) : 0.f, 0.f);
+            a[j] = make_float2(j < W ? windowed_sample(pcm + (long long)f * S, window, j, pre) : 0.f, 0.f);
         __syncthreads();
         // Stockham autosort, radix 2: stage with half-size l, stride m
         for (int l = N2 / 2, m = 1; l >= 1; l >>= 1, m <<= 1) {
@@ -87,27 +114,27 @@ __global__ void k_fft_mag_generic(const int16_t *__restrict__ pcm, const float *
 }
 
 void launch_fft_mag(const Derived &d, const FftTables &ft, const MelTables &mt, const int16_t *d_pcm, float *d_mag,
-                    int frames, cudaStream_t st)
+                    int frames, cudaStream_t st, float pre)
 {
     if (frames <= 0) return;
     const bool fast = (d.N2 == 512 || d.N2 == 256) && d.S % 2 == 0 && ft.N2 == d.N2 &&
                       (reinterpret_cast<uintptr_t>(d_pcm) & 3) == 0;
     if (fast) {
         const int R = d.M / 16, per_iter = 4 * (32 / R);
-        const int grid = std::min((frames + per_iter - 1) / per_iter, 148 * 8);
+        const int grid = std::min((frames + per_iter - 1) / per_iter, grid_cap(8));
         const bool pruned = d.W <= 26 * R;
         if (d.N2 == 512) {
-            if (pruned) k_fft_mag<512, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
-            else k_fft_mag<512, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+            if (pruned) k_fft_mag<512, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, pre);
+            else k_fft_mag<512, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, pre);
         } else {
-            if (pruned) k_fft_mag<256, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
-            else k_fft_mag<256, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S);
+            if (pruned) k_fft_mag<256, 13><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, pre);
+            else k_fft_mag<256, 16><<<grid, 128, 0, st>>>(d_pcm, mt.d_window2, ft.d_tw_a, ft.d_tw_p, d_mag, frames, d.S, pre);
         }
     } else {
         if (d.N2 > 4096) throw Error("window_size above 4096 is not supported");
         const int threads = std::max(32, std::min(256, d.N2 / 2));
-        k_fft_mag_generic<<<std::min(frames, 148 * 8), threads, sizeof(float2) * 2 * d.N2, st>>>(d_pcm, mt.d_window, d_mag,
-                                                                                                 frames, d.W, d.S, d.N2);
+        k_fft_mag_generic<<<std::min(frames, grid_cap(8)), threads, sizeof(float2) * 2 * d.N2, st>>>(d_pcm, mt.d_window, d_mag,
+                                                                                                 frames, d.W, d.S, d.N2, pre);
     }
     AFE_CUDA(cudaGetLastError());
     count_launch();
@@ -171,7 +198,7 @@ void launch_pad_rows(const float *d_src, float *d_dst, int rows, int dim, int le
 {
     const int total = (lead + rows + trail) * dim;
     if (total <= 0) return;
-    k_pad_rows<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(d_src, d_dst, rows, dim, lead, trail);
+    k_pad_rows<<<std::min((total + 255) / 256, grid_cap(8)), 256, 0, st>>>(d_src, d_dst, rows, dim, lead, trail);
     AFE_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -194,7 +221,7 @@ void launch_delta(const float *d_in, float *d_out, int rows, int dim, int L, cud
 {
     const int total = rows * dim;
     if (total <= 0) return;
-    k_delta<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(d_in, d_out, rows, dim, L);
+    k_delta<<<std::min((total + 255) / 256, grid_cap(8)), 256, 0, st>>>(d_in, d_out, rows, dim, L);
     AFE_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -242,6 +269,96 @@ void launch_colstats(const float *d_x, int rows, int dim, int norm_type, float *
     count_launch();
 }
 
+// ---- running record of a Normalizer (the statistics that corpus-level CMVN all-reduces): sum | sumsq | count | min | max
+__global__ void k_record_reset(double *rec, int dim)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < dim) { rec[c] = 0.0; rec[dim + c] = 0.0; rec[2 * dim + 1 + c] = (double)FLT_MAX; rec[3 * dim + 1 + c] = -(double)FLT_MAX; }
+    if (c == 0) rec[2 * dim] = 0.0;
+}
+// one CTA per column, same fixed-order tree as k_colstats; the column's totals are ADDED to the record (calls are stream ordered)
+__global__ void k_record_accumulate(const float *__restrict__ x, int rows, int dim, double *__restrict__ rec)
+{
+    __shared__ double s_sum[256], s_sq[256];
+    __shared__ float s_mn[256], s_mx[256];
+    const int c = blockIdx.x, t = threadIdx.x;
+    double s = 0.0, s2 = 0.0;
+    float mn = FLT_MAX, mx = -FLT_MAX;
+    for (int r = t; r < rows; r += blockDim.x) {
+        const float v = x[(long long)r * dim + c];
+        s += (double)v;
+        s2 += (double)__fmul_rn(v, v);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    s_sum[t] = s; s_sq[t] = s2; s_mn[t] = mn; s_mx[t] = mx;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (t < o) {
+            s_sum[t] += s_sum[t + o]; s_sq[t] += s_sq[t + o];
+            s_mn[t] = fminf(s_mn[t], s_mn[t + o]); s_mx[t] = fmaxf(s_mx[t], s_mx[t + o]);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        rec[c] += s_sum[0]; rec[dim + c] += s_sq[0];
+        rec[2 * dim + 1 + c] = fmin(rec[2 * dim + 1 + c], (double)s_mn[0]);
+        rec[3 * dim + 1 + c] = fmax(rec[3 * dim + 1 + c], (double)s_mx[0]);
+        if (c == 0) rec[2 * dim] += (double)rows;
+    }
+}
+__global__ void k_record_finalize(const double *__restrict__ rec, int dim, int norm_type, float *__restrict__ mean,
+                                  float *__restrict__ scale)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dim) return;
+    const double n = rec[2 * dim], s = rec[c], s2 = rec[dim + c];
+    const float mn = (float)rec[2 * dim + 1 + c], mx = (float)rec[3 * dim + 1 + c];
+    const float m = (float)(s / n);
+    mean[c] = m;
+    if (norm_type == AFE_NORM_CVN) scale[c] = (float)sqrt((n - 1.0) / (s2 - s * (s / n)));
+    else if (norm_type == AFE_NORM_MINMAX) scale[c] = 1.f / fmaxf(fabsf(mn - m), fabsf(mx - m));
+    else scale[c] = 1.f;
+}
+void launch_record_reset(double *d_rec, int dim, cudaStream_t st)
+{
+    k_record_reset<<<(dim + 127) / 128, 128, 0, st>>>(d_rec, dim);
+    AFE_CUDA(cudaGetLastError());
+    count_launch();
+}
+void launch_record_accumulate(const float *d_x, int rows, int dim, double *d_rec, cudaStream_t st)
+{
+    if (rows <= 0 || dim <= 0) return;
+    k_record_accumulate<<<dim, 256, 0, st>>>(d_x, rows, dim, d_rec);
+    AFE_CUDA(cudaGetLastError());
+    count_launch();
+}
+void launch_record_finalize(const double *d_rec, int dim, int norm_type, float *d_mean, float *d_scale, cudaStream_t st)
+{
+    k_record_finalize<<<(dim + 127) / 128, 128, 0, st>>>(d_rec, dim, norm_type, d_mean, d_scale);
+    AFE_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void NormState::init(int t, int d)
+{
+    type = t; dim = d;
+    mean.alloc(d); scale.alloc(d); rec.alloc(4 * (size_t)d + 1);
+}
+void NormState::normalize(float *d_x, int rows, bool use_last, cudaStream_t st)   // normalizercpu.cpp:22-89
+{
+    if (type == AFE_NORM_NONE || rows <= 0) return;
+    if (!use_last) launch_colstats(d_x, rows, dim, type, mean.p, scale.p, st);
+    launch_affine(d_x, rows, dim, type, mean.p, scale.p, st);
+}
+void NormState::reset_record(cudaStream_t st) { launch_record_reset(rec.p, dim, st); }
+void NormState::accumulate(const float *d_x, int rows, cudaStream_t st) { launch_record_accumulate(d_x, rows, dim, rec.p, st); }
+void NormState::finalize(cudaStream_t st) { launch_record_finalize(rec.p, dim, type, mean.p, scale.p, st); }
+void NormState::apply(float *d_x, int rows, cudaStream_t st)
+{
+    if (type == AFE_NORM_NONE || rows <= 0) return;
+    launch_affine(d_x, rows, dim, type, mean.p, scale.p, st);
+}
+
 __global__ void k_affine(float *__restrict__ x, int rows, int dim, int norm_type, const float *__restrict__ mean,
                          const float *__restrict__ scale)
 {
@@ -256,7 +373,7 @@ void launch_affine(float *d_x, int rows, int dim, int norm_type, const float *d_
 {
     const long long total = (long long)rows * dim;
     if (total <= 0) return;
-    k_affine<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(d_x, rows, dim, norm_type, d_mean, d_scale);
+    k_affine<<<(int)std::min<long long>((total + 255) / 256, grid_cap(8)), 256, 0, st>>>(d_x, rows, dim, norm_type, d_mean, d_scale);
     AFE_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -277,7 +394,7 @@ void launch_pack(const float *d_s, const float *d_d1, const float *d_d2, float *
 {
     const int total = rows * cols * nstreams;
     if (total <= 0) return;
-    k_pack<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(d_s, d_d1, d_d2, d_out, rows, cols, nstreams);
+    k_pack<<<std::min((total + 255) / 256, grid_cap(8)), 256, 0, st>>>(d_s, d_d1, d_d2, d_out, rows, cols, nstreams);
     AFE_CUDA(cudaGetLastError());
     count_launch();
 }

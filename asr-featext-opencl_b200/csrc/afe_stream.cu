@@ -1,29 +1,20 @@
 // Streaming objects of the C ABI: afe_mfcc (MfccOpenCL replacement), afe_segmenter, afe_delta, afe_normalizer.
-// Host-side state machines follow the reference CPU classes (segmentercpu.cpp:56-106, mfcccpu.cpp:338-444); all
-// arithmetic runs in the CUDA kernels of afe_stages.cu. One CUDA stream per object; every verb returns after the
-// data it hands back is valid on the host (like the blocking reads of the OpenCL classes, mfccopencl.cpp:78-90).
+// Host-side state machines follow the reference CPU classes (segmentercpu.cpp:56-106, mfcccpu.cpp:338-444).
+// afe_mfcc runs every block through the fused kernel K1 (afe_fused.cuh): ONE launch per apply(), the block being a
+// "tile group" with its carried-over context as halo; parameter sets K1 does not cover (other FFT sizes, odd shifts,
+// normalisation before the deltas) take the staged kernels of afe_stages.cu. One CUDA stream per object; a verb only
+// waits for the device where it hands data back to the host (get_output, like the blocking reads of mfccopencl.cpp:78-90).
 #include <algorithm>
 #include <cstring>
 #include <memory>
 
 #include "afe_internal.h"
+#include "afe_fused_host.h"
+#include "afe_nccl.h"
 
 using namespace afe;
 
 namespace {
-
-template <class T> struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    void alloc(size_t count)
-    {
-        release();
-        n = count;
-        AFE_CUDA(cudaMalloc(&p, sizeof(T) * std::max<size_t>(count, 1)));
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    ~DevBuf() { release(); }
-};
 
 // Carry-over bookkeeping shared by afe_segmenter and afe_mfcc (segmentercpu.cpp). PCM lives on the device in two
 // ping-pong buffers: `cur` holds [carry-over | new block]; after the frames are cut the tail is copied to the front
@@ -34,9 +25,13 @@ struct SegState {
     bool flushed = true, last_calc_flushed = false;
     size_t cap = 0;
     DevBuf<int16_t> buf[2];
-    int16_t *h_pin = nullptr; // pinned staging so the H2D copy is truly asynchronous and the caller may reuse its buffer
+    // pinned staging (two buffers, alternating) so that the H2D copy is asynchronous and the caller may reuse its buffer
+    // at once; a buffer is reused only after the copy that read it has completed (event), which by then it normally has
+    int16_t *h_pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pin[2] = {nullptr, nullptr};
     size_t pin_cap = 0;
-    int cur = 0;
+    int cur = 0, pin = 0;
+    float pre = 0.f;          // pre-emphasis coefficient (staged segmenter path)
 
     void init(int W_, int S_, int frame_cap_, int D_)
     {
@@ -48,13 +43,19 @@ struct SegState {
             AFE_CUDA(cudaMemset(b.p, 0, sizeof(int16_t) * (cap + N2 + 16)));
         }
         pin_cap = cap;
-        AFE_CUDA(cudaMallocHost(&h_pin, sizeof(int16_t) * std::max<size_t>(pin_cap, 1)));
+        for (int i = 0; i < 2; i++) {
+            AFE_CUDA(cudaMallocHost(&h_pin[i], sizeof(int16_t) * std::max<size_t>(pin_cap, 1)));
+            AFE_CUDA(cudaEventCreateWithFlags(&ev_pin[i], cudaEventDisableTiming));
+        }
     }
     void release()
     {
         buf[0].release(); buf[1].release();
-        if (h_pin) cudaFreeHost(h_pin);
-        h_pin = nullptr;
+        for (int i = 0; i < 2; i++) {
+            if (h_pin[i]) cudaFreeHost(h_pin[i]);
+            if (ev_pin[i]) cudaEventDestroy(ev_pin[i]);
+            h_pin[i] = nullptr; ev_pin[i] = nullptr;
+        }
     }
     void reset() { remaining = samples = 0; flushed = true; last_calc_flushed = false; }
     int est(int n) const { return afe_estimated_window_count(n, W, S); }
@@ -63,23 +64,31 @@ struct SegState {
     const int16_t *set_input(const int16_t *in, int n, int &wc, int &wc_nd, cudaStream_t st)
     {
         if ((size_t)n + (flushed ? 0 : remaining) > cap) throw Error("Can't process data, buffer is too small");
-        last_calc_flushed = flushed;
-        AFE_CUDA(cudaStreamSynchronize(st));                 // h_pin may still feed the previous copy
-        memcpy(h_pin, in, sizeof(int16_t) * n);
         int16_t *dst = buf[cur].p;
-        int total;
+        int total = n;
         if (flushed) {                                       // first block of a stream (segmentercpu.cpp:59-75)
-            AFE_CUDA(cudaMemcpyAsync(dst, h_pin, sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
             total = n;
             wc_nd = est(total);
             wc = wc_nd - D;
-            if (wc <= 0) throw Error("Can't process data, window count is too small");
+            // wc < D would put the carry-over in front of the buffer (the reference reads out of bounds there,
+            // segmentercpu.cpp:69-73): same error as for wc <= 0
+            if (wc <= 0 || wc < D) throw Error("Can't process data, window count is too small");
             const int used = (wc - D) * S + W - S;
             if (used <= 0) throw Error("Processed samples <= 0, this should never happen");
+        }
+        last_calc_flushed = flushed;
+        pin ^= 1;
+        AFE_CUDA(cudaEventSynchronize(ev_pin[pin]));         // the copy that last read this staging buffer is done
+        memcpy(h_pin[pin], in, sizeof(int16_t) * n);
+        if (flushed) {
+            AFE_CUDA(cudaMemcpyAsync(dst, h_pin[pin], sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
+            AFE_CUDA(cudaEventRecord(ev_pin[pin], st));
+            const int used = (wc - D) * S + W - S;
             remaining = total - used + W - S;
             flushed = false;
         } else {                                             // append to the carry-over (segmentercpu.cpp:76-93)
-            AFE_CUDA(cudaMemcpyAsync(dst + remaining, h_pin, sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
+            AFE_CUDA(cudaMemcpyAsync(dst + remaining, h_pin[pin], sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
+            AFE_CUDA(cudaEventRecord(ev_pin[pin], st));
             total = n + remaining;
             wc_nd = est(total);
             wc = wc_nd - 2 * D;
@@ -106,18 +115,6 @@ struct SegState {
     }
 };
 
-struct NormState {
-    int type = AFE_NORM_NONE, dim = 0;
-    DevBuf<float> mean, scale;
-    void init(int t, int d) { type = t; dim = d; mean.alloc(d); scale.alloc(d); }
-    void normalize(float *d_x, int rows, bool use_last, cudaStream_t st)   // normalizercpu.cpp:22-89
-    {
-        if (type == AFE_NORM_NONE || rows <= 0) return;
-        if (!use_last) launch_colstats(d_x, rows, dim, type, mean.p, scale.p, st);
-        launch_affine(d_x, rows, dim, type, mean.p, scale.p, st);
-    }
-};
-
 } // namespace
 
 // ================================================================================================== afe_mfcc
@@ -125,20 +122,53 @@ struct afe_mfcc {
     Derived d;
     int device;
     cudaStream_t st = nullptr;
+    SegState seg;
+    float alpha = 1.f, pre = 0.f;
+    bool window_set = false, last_block = false, fix_q1 = false;
+    std::vector<float> window;
+    DevBuf<float> outb;
+    float *h_out = nullptr; size_t h_out_cap = 0;
+    // ---- fused route: every block is ONE launch of K1
+    std::unique_ptr<FusedEngine> eng;
+    const int16_t *blk_pcm = nullptr;   // device PCM of the current block (carry-over + new samples)
+    DevBuf<Tile> d_tiles;
+    Tile *h_tiles = nullptr; size_t tiles_cap = 0;
+    cudaEvent_t ev_tiles = nullptr;     // the tile upload of the previous apply() has been consumed
+    DevBuf<double> partials;
+    DevBuf<int> counters;               // [1] arrival tickets + [1] role tickets
+    DevBuf<unsigned> flags;
+    unsigned epoch = 0;
+    DevBuf<float> g_mean, g_scale;      // statistics of the last normalised block (use_last_stats for the flush block)
+    int launches = 0;
+    // ---- staged route (parameter sets K1 does not cover): one kernel per reference stage, spectrum persisted
     FftTables fft;
     MelTables mel;
-    SegState seg;
     NormState n0, n1, n2;
-    float alpha = 1.f;
-    bool window_set = false, last_block = false, fix_q1 = false;
-    DevBuf<float> mag, melv, cep, dpad, d1, d2, outb;
-    float *h_out = nullptr; size_t h_out_cap = 0;
+    DevBuf<float> mag, melv, cep, dpad, d1, d2;
     afe_mfcc(const afe_params &p, int dev) : d(p), device(dev) {}
+    bool fused() const { return (bool)eng; }
     float *statics() { return d.C > 0 ? cep.p : melv.p; }
     // Row offset of this block's first OUTPUT static: the reference keys it on was_flushed() (mfcccpu.cpp:274,439),
     // which is still true when flushing after a single set_input (quirk Q1) unless the fix is requested.
     int static_row_offset() const { return (!seg.last_calc_flushed || (fix_q1 && last_block)) ? d.D : 0; }
 };
+
+// buffers of the staged route (one kernel per reference stage)
+static void alloc_staged(afe_mfcc *h)
+{
+    const Derived &d = h->d;
+    const size_t fc = d.frame_cap;
+    if (d.N2 == 512 || d.N2 == 256) h->fft.build(d.N2);
+    h->mag.alloc(fc * d.bins);
+    h->melv.alloc(fc * d.nb);
+    if (d.C > 0) h->cep.alloc(fc * d.dct_len);
+    if (d.p.norm != AFE_NORM_NONE) { h->n0.init(d.p.norm, d.cols); h->n1.init(d.p.norm, d.cols); h->n2.init(d.p.norm, d.cols); }
+    if (d.p.dyn != AFE_DYN_NONE) {
+        h->dpad.alloc((fc + 2 * d.D) * d.cols);          // m_delta_in, mfcccpu.cpp:148-156
+        h->d1.alloc((fc + 2 * d.l2) * d.cols);
+        h->d2.alloc(fc * d.cols);
+    }
+}
 
 extern "C" {
 
@@ -152,18 +182,26 @@ int afe_mfcc_create(const afe_params *p, int cuda_device, afe_mfcc **out)
         if (d.in_frames_cap < 1) throw Error("input_buffer_size is smaller than one window");
         DeviceGuard g(cuda_device);
         AFE_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-        if (d.N2 == 512 || d.N2 == 256) h->fft.build(d.N2);
         h->seg.init(d.W, d.S, d.frame_cap, d.D);
         const size_t fc = d.frame_cap;
-        h->mag.alloc(fc * d.bins);
-        h->melv.alloc(fc * d.nb);
-        if (d.C > 0) h->cep.alloc(fc * d.dct_len);
-        if (d.p.norm != AFE_NORM_NONE) { h->n0.init(d.p.norm, d.cols); h->n1.init(d.p.norm, d.cols); h->n2.init(d.p.norm, d.cols); }
-        if (d.p.dyn != AFE_DYN_NONE) {
-            h->dpad.alloc((fc + 2 * d.D) * d.cols);          // m_delta_in, mfcccpu.cpp:148-156
-            h->d1.alloc((fc + 2 * d.l2) * d.cols);
-            h->d2.alloc(fc * d.cols);
-        }
+        // K1 covers the block when the parameter set fits it and normalisation (if any) comes after the deltas: normalising
+        // BEFORE them takes statistics over the look-ahead rows of the block as well (mfcccpu.cpp:383-384), which no tile owns
+        const bool fused = fused_unsupported_reason(d).empty() && (d.p.norm == AFE_NORM_NONE || d.p.norm_after_dyn);
+        if (fused) {
+            h->eng.reset(new FusedEngine(d, cuda_device));
+            h->tiles_cap = fc / std::max(1, h->eng->nout_max / 2) + 8;
+            h->d_tiles.alloc(h->tiles_cap);
+            AFE_CUDA(cudaMallocHost(&h->h_tiles, sizeof(Tile) * h->tiles_cap));
+            AFE_CUDA(cudaEventCreateWithFlags(&h->ev_tiles, cudaEventDisableTiming));
+            if (d.p.norm != AFE_NORM_NONE) {
+                h->partials.alloc(h->tiles_cap * 4 * d.width);
+                h->counters.alloc(2); h->flags.alloc(1);
+                AFE_CUDA(cudaMemset(h->counters.p, 0, sizeof(int) * 2));
+                AFE_CUDA(cudaMemset(h->flags.p, 0, sizeof(unsigned)));
+                h->g_mean.alloc(d.width); h->g_scale.alloc(d.width);
+            }
+        } else
+            alloc_staged(h.get());
         h->outb.alloc(fc * d.width);
         h->h_out_cap = fc * d.width;
         AFE_CUDA(cudaMallocHost(&h->h_out, sizeof(float) * h->h_out_cap));
@@ -176,23 +214,49 @@ void afe_mfcc_destroy(afe_mfcc *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
+    h->eng.reset();
     h->fft.release(); h->mel.release(); h->seg.release();
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_tiles) cudaFreeHost(h->h_tiles);
+    if (h->ev_tiles) cudaEventDestroy(h->ev_tiles);
     cudaStreamDestroy(h->st);
     delete h;
 }
 
 int afe_mfcc_set_window(afe_mfcc *h, const float *window)
 {
-    return guarded([&] { DeviceGuard g(h->device); upload_window(h->d, window, h->mel, h->st); h->window_set = true; });
+    return guarded([&] {
+        DeviceGuard g(h->device);
+        if (h->fused()) h->eng->set_window(window, h->st);
+        else upload_window(h->d, window, h->mel, h->st);
+        h->window_set = true;
+    });
 }
 int afe_mfcc_set_alpha(afe_mfcc *h, float alpha) { h->alpha = alpha; return 0; }
+int afe_mfcc_set_preemphasis(afe_mfcc *h, float coefficient)
+{
+    return guarded([&] {
+        if (!(coefficient >= 0.f && coefficient < 1.f)) throw Error("pre-emphasis coefficient must be in [0, 1)");
+        h->pre = coefficient;
+        if (h->fused()) h->eng->pre = coefficient;
+    });
+}
 int afe_mfcc_input_buffer_size(const afe_mfcc *h) { return h->d.in_cap; }
 int afe_mfcc_estimated_window_count(const afe_mfcc *h, int samples) { return afe_estimated_window_count(samples, h->d.W, h->d.S); }
 int afe_mfcc_output_width(const afe_mfcc *h) { return h->d.width; }
+int afe_mfcc_uses_fused_kernel(const afe_mfcc *h) { return h->fused() ? 1 : 0; }
+int afe_mfcc_kernel_launches(const afe_mfcc *h) { return h->launches; }
 int afe_mfcc_set_option(afe_mfcc *h, int option, int value)
 {
     if (option == AFE_OPT_FIX_FLUSH_STATICS) { h->fix_q1 = value != 0; return 0; }
+    if (option == AFE_OPT_STAGED_KERNELS) {
+        // A-B switch: run the blocks through the staged kernels although the fused kernel covers the parameter set
+        return guarded([&] {
+            if (h->window_set) throw Error("AFE_OPT_STAGED_KERNELS must be set before set_window");
+            if (value != 0 && h->fused()) { DeviceGuard g(h->device); h->eng.reset(); alloc_staged(h); }
+            else if (value == 0 && !h->fused()) throw Error("the staged kernels cannot be switched off for this parameter set");
+        });
+    }
     return fail("unknown option");
 }
 int afe_mfcc_reset(afe_mfcc *h)
@@ -209,7 +273,8 @@ int afe_mfcc_set_input(afe_mfcc *h, const int16_t *data, int samples, int *frame
         DeviceGuard g(h->device);
         int wc, wc_nd;
         const int16_t *pcm = h->seg.set_input(data, samples, wc, wc_nd, h->st);
-        if (wc > 0) launch_fft_mag(h->d, h->fft, h->mel, pcm, h->mag.p, wc_nd, h->st);      // segment + fft fused
+        h->blk_pcm = pcm; // stays intact in its ping-pong buffer until the set_input after the next one
+        if (!h->fused() && wc > 0) launch_fft_mag(h->d, h->fft, h->mel, pcm, h->mag.p, wc_nd, h->st, h->pre); // segment + fft fused
         h->seg.carry(h->st);
         *frames = wc > 0 ? wc : 0;
     });
@@ -224,8 +289,9 @@ int afe_mfcc_flush(afe_mfcc *h, int *frames)
         DeviceGuard g(h->device);
         int wc, wc_nd;
         const int16_t *pcm = h->seg.flush(wc, wc_nd);
+        h->blk_pcm = pcm;
         if (wc <= 0) return;
-        launch_fft_mag(h->d, h->fft, h->mel, pcm, h->mag.p, wc_nd, h->st);
+        if (!h->fused()) launch_fft_mag(h->d, h->fft, h->mel, pcm, h->mag.p, wc_nd, h->st, h->pre);
         *frames = wc;
     });
 }
@@ -258,6 +324,51 @@ static void normalise(afe_mfcc *h, int wc, bool use_last)
         h->n0.normalize(src, wc, use_last, h->st);
 }
 
+// One block through K1. The block's device PCM holds wc_nd frames; its output rows are the frames [t_first, t_first + wc):
+//   first block   t_first = 0, left edge replicated by index clamping, D look-ahead frames on the right
+//   middle block  t_first = D, context on both sides comes from the carried-over samples
+//   flush block   t_first = D, right edge replicated; normalised with the previous block's statistics
+// (mfcccpu.cpp:371-425; do_delta :234-263). Rows land in outb[0 .. wc).
+static void apply_fused(afe_mfcc *h, int wc, int wc_nd, bool first, bool last)
+{
+    const Derived &d = h->d;
+    FusedEngine &eng = *h->eng;
+    eng.ensure_mel(h->alpha);
+    const int t_first = first ? 0 : d.D;
+    std::vector<Tile> tiles;
+    const int ntiles = eng.plan_rows(tiles, 0, -(long long)t_first, wc_nd, t_first, wc, 0);
+    if ((size_t)ntiles > h->tiles_cap) throw Error("block needs more tiles than the object was sized for");
+    AFE_CUDA(cudaEventSynchronize(h->ev_tiles));             // the previous upload has left the pinned table
+    memcpy(h->h_tiles, tiles.data(), sizeof(Tile) * ntiles);
+    AFE_CUDA(cudaMemcpyAsync(h->d_tiles.p, h->h_tiles, sizeof(Tile) * ntiles, cudaMemcpyHostToDevice, h->st));
+    AFE_CUDA(cudaEventRecord(h->ev_tiles, h->st));
+    const bool tma = d.S % 8 == 0 && (reinterpret_cast<uintptr_t>(h->blk_pcm) & 15) == 0;
+    // quirk Q1: flushing after a single set_input reads every static D rows early (static_row_offset() == 0 there)
+    const int q1 = (last && h->static_row_offset() == 0) ? 2 : 0;
+    FusedArgs a = eng.base_args(q1, tma);
+    a.pcm = h->blk_pcm; a.out = h->outb.p; a.tiles = h->d_tiles.p; a.tile_base = 0;
+    int grid = ntiles, cluster = 0;
+    if (d.p.norm != AFE_NORM_NONE) {
+        a.g_mean = h->g_mean.p; a.g_scale = h->g_scale.p;
+        if (last) a.use_last = 1;                             // mfcccpu.cpp:389: use_last_stats
+        else {
+            a.stats_rows_mode = 3; a.stats_count = wc;        // this block's output rows (normalizercpu.cpp:22-30)
+            a.stats_kind = d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3;
+            a.partials = h->partials.p;
+            const bool fast3 = d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
+            if (fast3 && ntiles <= 4 && eng.cluster_schedulable(ntiles, a, h->st)) { a.cluster_norm = 1; cluster = ntiles; }
+            else if (ntiles <= 8) a.counters = h->counters.p;
+            else {
+                a.counters = h->counters.p; a.work_counter = h->counters.p + 1;
+                a.flags = h->flags.p; a.epoch = ++h->epoch; a.ntiles_launch = ntiles;
+                grid = 2 * ntiles;
+            }
+        }
+    }
+    eng.launch(a, grid, cluster, h->st);
+    h->launches++;
+}
+
 int afe_mfcc_apply(afe_mfcc *h)
 {
     return guarded([&] {
@@ -275,12 +386,17 @@ int afe_mfcc_apply(afe_mfcc *h)
             wc_nd = h->seg.est(h->seg.samples); wc = wc_nd - 2 * d.D;
             if (wc <= 0) return;
         }
+        if (h->fused()) { apply_fused(h, wc, wc_nd, first, last); return; }
         if (h->mel.alpha_built != h->alpha) upload_mel_tables(d, h->alpha, h->mel, h->st);  // refresh_filters per alpha
         launch_mel_dct(d, h->mel, h->mag.p, h->melv.p, h->cep.p, wc_nd, h->st);
         const bool norm = d.p.norm != AFE_NORM_NONE;
         if (!d.p.norm_after_dyn && norm) normalise(h, wc_nd, use_last);
         if (d.p.dyn != AFE_DYN_NONE) dynamics(h, wc, first, last);
         if (d.p.norm_after_dyn && norm) normalise(h, wc, use_last);
+        // rows -> outb, so that get_output is one copy on either route
+        const float *s0 = h->statics() + h->static_row_offset() * d.cols;
+        const int ns = d.width / d.cols;
+        launch_pack(s0, ns > 1 ? h->d1.p + d.l2 * d.cols : nullptr, ns > 2 ? h->d2.p : nullptr, h->outb.p, wc, d.cols, ns, h->st);
     });
 }
 
@@ -291,9 +407,6 @@ int afe_mfcc_get_output(afe_mfcc *h, float *out, int frames)
         if (frames > d.frame_cap) throw Error("Window count too high");   // mfcccpu.cpp:429-430
         if (frames <= 0) return;
         DeviceGuard g(h->device);
-        const float *s0 = h->statics() + h->static_row_offset() * d.cols;
-        const int ns = d.width / d.cols;
-        launch_pack(s0, ns > 1 ? h->d1.p + d.l2 * d.cols : nullptr, ns > 2 ? h->d2.p : nullptr, h->outb.p, frames, d.cols, ns, h->st);
         const size_t n = (size_t)frames * d.width;
         AFE_CUDA(cudaMemcpyAsync(h->h_out, h->outb.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->st));
         AFE_CUDA(cudaStreamSynchronize(h->st));
@@ -315,11 +428,6 @@ struct afe_delta {
     int device, dim, window_limit, L;
     cudaStream_t st = nullptr;
     DevBuf<float> out;
-};
-struct afe_normalizer {
-    int device;
-    cudaStream_t st = nullptr;
-    NormState ns;
 };
 
 extern "C" {
@@ -361,7 +469,7 @@ int afe_segmenter_set_input(afe_segmenter *s, const int16_t *in, float *d_out, i
         if (!s->window_set) throw Error("set_window must be called before set_input");
         DeviceGuard g(s->device);
         const int16_t *pcm = s->seg.set_input(in, samples, *wc, *wc_nd, s->st);
-        if (*wc > 0) launch_segment(pcm, s->window.p, d_out, *wc_nd, s->seg.W, s->seg.S, s->seg.N2, s->st);
+        if (*wc > 0) launch_segment(pcm, s->window.p, d_out, *wc_nd, s->seg.W, s->seg.S, s->seg.N2, s->st, s->seg.pre);
         s->seg.carry(s->st);
         AFE_CUDA(cudaStreamSynchronize(s->st));
     });
@@ -371,8 +479,15 @@ int afe_segmenter_flush(afe_segmenter *s, float *d_out, int *wc, int *wc_nd)
     return guarded([&] {
         DeviceGuard g(s->device);
         const int16_t *pcm = s->seg.flush(*wc, *wc_nd);
-        if (*wc > 0) launch_segment(pcm, s->window.p, d_out, *wc_nd, s->seg.W, s->seg.S, s->seg.N2, s->st);
+        if (*wc > 0) launch_segment(pcm, s->window.p, d_out, *wc_nd, s->seg.W, s->seg.S, s->seg.N2, s->st, s->seg.pre);
         AFE_CUDA(cudaStreamSynchronize(s->st));
+    });
+}
+int afe_segmenter_set_preemphasis(afe_segmenter *s, float coefficient)
+{
+    return guarded([&] {
+        if (!(coefficient >= 0.f && coefficient < 1.f)) throw Error("pre-emphasis coefficient must be in [0, 1)");
+        s->seg.pre = coefficient;
     });
 }
 int afe_segmenter_remaining_samples(const afe_segmenter *s) { return s->seg.remaining; }
@@ -417,11 +532,14 @@ int afe_normalizer_create(int norm_type, int dim, int cuda_device, afe_normalize
     *out = nullptr;
     return guarded([&] {
         if (afe_device_count() <= cuda_device) throw Error("no usable CUDA device (the product has no CPU fallback)");
+        if (norm_type < AFE_NORM_NONE || norm_type > AFE_NORM_MINMAX || dim < 1) throw Error("invalid normalizer arguments");
         std::unique_ptr<afe_normalizer> n(new afe_normalizer());
         n->device = cuda_device;
         DeviceGuard g(cuda_device);
-        AFE_CUDA(cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking));
+        AFE_CUDA(cudaStreamCreateWithFlags(&n->own_st, cudaStreamNonBlocking));
+        n->st = n->own_st;
         n->ns.init(norm_type, dim);
+        n->ns.reset_record(n->st);
         *out = n.release();
     });
 }
@@ -429,16 +547,72 @@ void afe_normalizer_destroy(afe_normalizer *n)
 {
     if (!n) return;
     cudaSetDevice(n->device);
-    cudaStreamSynchronize(n->st);
-    cudaStreamDestroy(n->st);
+    cudaStreamSynchronize(n->own_st);
+    cudaStreamDestroy(n->own_st);
     delete n;
 }
+static cudaStream_t norm_stream(afe_normalizer *n) { return n->st ? n->st : n->own_st; }
+
 int afe_normalizer_normalize(afe_normalizer *n, float *d_data, int offset, int window_count, int use_last_stats)
 {
     return guarded([&] {
         DeviceGuard g(n->device);
-        n->ns.normalize(d_data + offset, window_count, use_last_stats != 0, n->st);
-        AFE_CUDA(cudaStreamSynchronize(n->st));
+        n->ns.normalize(d_data + offset, window_count, use_last_stats != 0, norm_stream(n));
+        AFE_CUDA(cudaStreamSynchronize(norm_stream(n)));
+    });
+}
+
+// ---- corpus-level statistics: the verbs of the OpenCL class' three kernels (norm.cl kernelSum / kernelFinalizeSum /
+// kernelNormalize, normalizeropencl.cpp:123-158) exposed one by one, with the all-reduce between the first two.
+int afe_normalizer_stats_len(const afe_normalizer *n) { return n->ns.rec_len(); }
+int afe_normalizer_reset(afe_normalizer *n)
+{
+    return guarded([&] { DeviceGuard g(n->device); n->ns.reset_record(norm_stream(n)); });
+}
+int afe_normalizer_accumulate(afe_normalizer *n, const float *d_data, int offset, int window_count)
+{
+    return guarded([&] {
+        if (window_count < 0) throw Error("accumulate: negative window count");
+        DeviceGuard g(n->device);
+        n->ns.accumulate(d_data + offset, window_count, norm_stream(n));
+    });
+}
+int afe_normalizer_allreduce(afe_normalizer *n, void *nccl_comm)
+{
+    return guarded([&] {
+        DeviceGuard g(n->device);
+        const int w = n->ns.dim;
+        double *rec = n->ns.rec.p;
+        // one NCCL group: sums + count (ncclSum), minima (ncclMin), maxima (ncclMax) — 4*dim+1 doubles, latency bound
+        nccl_allreduce_stats(nccl_comm, rec, 2 * w + 1, rec + 2 * w + 1, w, rec + 3 * w + 1, w, norm_stream(n));
+    });
+}
+int afe_normalizer_finalize(afe_normalizer *n)
+{
+    return guarded([&] { DeviceGuard g(n->device); n->ns.finalize(norm_stream(n)); });
+}
+int afe_normalizer_apply(afe_normalizer *n, float *d_data, int offset, int window_count)
+{
+    return guarded([&] {
+        DeviceGuard g(n->device);
+        n->ns.apply(d_data + offset, window_count, norm_stream(n));
+        AFE_CUDA(cudaStreamSynchronize(norm_stream(n)));
+    });
+}
+int afe_normalizer_get_stats(afe_normalizer *n, double *h_stats)
+{
+    return guarded([&] {
+        DeviceGuard g(n->device);
+        AFE_CUDA(cudaMemcpyAsync(h_stats, n->ns.rec.p, sizeof(double) * n->ns.rec_len(), cudaMemcpyDeviceToHost, norm_stream(n)));
+        AFE_CUDA(cudaStreamSynchronize(norm_stream(n)));
+    });
+}
+int afe_normalizer_set_stats(afe_normalizer *n, const double *h_stats)
+{
+    return guarded([&] {
+        DeviceGuard g(n->device);
+        AFE_CUDA(cudaMemcpyAsync(n->ns.rec.p, h_stats, sizeof(double) * n->ns.rec_len(), cudaMemcpyHostToDevice, norm_stream(n)));
+        AFE_CUDA(cudaStreamSynchronize(norm_stream(n)));
     });
 }
 

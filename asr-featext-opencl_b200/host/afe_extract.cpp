@@ -23,7 +23,7 @@
 #include "mfcccuda.hpp"
 
 struct Config { // SConfig, ASR_OCL.cpp:81-100; defaults ASR_OCL.cpp:560
-    float alpha = 1.f, window_ms = 25.f, shift_ms = 10.f;
+    float alpha = 1.f, alpha_max = 1.f, alpha_step = 0.f, preemphasis = 0.f, window_ms = 25.f, shift_ms = 10.f;
     int num_banks = 15, ceps_len = 12, norm_type = 2, dyn_type = 0, delta_l1 = 3, delta_l2 = 3;
     float sample_rate = 16000.f, low_freq = 64.f, high_freq = 0.f, lift_coef = 22.f;
     bool want_c0 = true, norm_after_dyn = true, text_output = true, fix_flush = false, batch = false, htk = false;
@@ -90,41 +90,61 @@ static void write_rows(FILE *fout, const Config &cfg, const float *data, int row
     }
 }
 
+// VTLN sweep of the reference driver (ASR_OCL.cpp:198-218): alpha = min, min + step, ... <= max; one output file per alpha,
+// named stem + to_string(alpha) + extension when there is more than one.
+static std::vector<float> alpha_list(const Config &cfg)
+{
+    std::vector<float> a;
+    if (cfg.alpha_step <= 0.f || cfg.alpha_max - cfg.alpha < cfg.alpha_step) { a.push_back(cfg.alpha); return a; }
+    int i = 0;
+    for (float v = cfg.alpha; v <= cfg.alpha_max; v = cfg.alpha + i * cfg.alpha_step) { a.push_back(v); i++; }
+    return a;
+}
+
 static void process_file(ParamBase *param, const Config &cfg, const std::string &in, const std::string &out)
 {
     std::vector<short> pcm = read_pcm(in);
-    FILE *fout = fopen(out.c_str(), cfg.text_output && !cfg.htk ? "w" : "wb");
-    if (!fout) throw std::runtime_error("Can't create output file: " + out);
+    const std::vector<float> alphas = alpha_list(cfg);
+    std::vector<FILE *> fouts;
+    for (float alpha : alphas) {
+        std::string name = out;
+        if (alphas.size() > 1 && out.size() > 4) name = out.substr(0, out.size() - 4) + std::to_string(alpha) + out.substr(out.size() - 4);
+        FILE *f = fopen(name.c_str(), cfg.text_output && !cfg.htk ? "w" : "wb");
+        if (!f) throw std::runtime_error("Can't create output file: " + name);
+        fouts.push_back(f);
+    }
     const int limit = param->get_input_buffer_size(), width = param->get_output_data_width();
-    if (cfg.htk) write_htk_header(fout, cfg, 0, width);
+    if (cfg.htk) for (FILE *f : fouts) write_htk_header(f, cfg, 0, width);
     // a middle block can return more rows than estimated_window_count(limit) (carry-over): size for the object's frame
     // capacity, input_window_limit + 2 + 3*(l1+l2) (mfcccpu.cpp:95-103)
     std::vector<float> rows((size_t)width * (size_t)(std::max(1, param->estimated_window_count(limit)) + 2 + 3 * (cfg.delta_l1 + cfg.delta_l2)));
     long total = 0;
     size_t pos = 0;
+    // one set_input, then set_alpha -> apply -> get_output_data per alpha (ASR_OCL.cpp:234-243): set_alpha is the
+    // NON-virtual ParamBase member, called through the base pointer exactly as the reference driver does
+    auto emit = [&](int wc) {
+        for (size_t k = 0; k < alphas.size(); k++) {
+            param->set_alpha(alphas[k]);
+            param->apply();
+            param->get_output_data(rows.data(), wc);
+            write_rows(fouts[k], cfg, rows.data(), wc, width, total);
+        }
+        total += wc;
+    };
     while (pos < pcm.size()) { // ASR_OCL.cpp:227-267
         const int n = (int)std::min<size_t>(pcm.size() - pos, (size_t)limit);
         const int wc = param->set_input(pcm.data() + pos, n);
-        param->set_alpha(cfg.alpha);
-        param->apply();
-        if (wc > 0) {
-            param->get_output_data(rows.data(), wc);
-            write_rows(fout, cfg, rows.data(), wc, width, total);
-            total += wc;
-        }
+        if (wc > 0) emit(wc);
+        else { param->set_alpha(alphas[0]); param->apply(); }
         pos += n;
     }
     const int wc = param->flush(); // ASR_OCL.cpp:268-301
-    if (wc > 0) {
-        param->set_alpha(cfg.alpha);
-        param->apply();
-        param->get_output_data(rows.data(), wc);
-        write_rows(fout, cfg, rows.data(), wc, width, total);
-        total += wc;
+    if (wc > 0) emit(wc);
+    for (FILE *f : fouts) {
+        if (cfg.htk) write_htk_header(f, cfg, total, width);
+        fclose(f);
     }
-    if (cfg.htk) write_htk_header(fout, cfg, total, width);
-    fclose(fout);
-    fprintf(stderr, "%s: %ld frames x %d -> %s\n", in.c_str(), total, width, out.c_str());
+    fprintf(stderr, "%s: %ld frames x %d x %zu alpha(s) -> %s\n", in.c_str(), total, width, alphas.size(), out.c_str());
 }
 
 // --batch: every file is one utterance of ONE shard (each processed like a file that fits a single block of the reference
@@ -153,6 +173,7 @@ static void process_batch(const Config &cfg, const std::vector<std::string> &fil
     try {
         check(afe_batch_set_window(b, window));
         check(afe_batch_set_alpha(b, cfg.alpha));
+        if (cfg.preemphasis > 0.f) check(afe_batch_set_preemphasis(b, cfg.preemphasis));
         check(afe_batch_set_options(b, AFE_STATS_REFERENCE_BLOCK, cfg.fix_flush ? 0 : AFE_BATCH_Q1_EXACT));
         int64_t total = 0;
         check(afe_batch_plan(b, off.data(), len.data(), (int)n, &total));
@@ -192,7 +213,10 @@ int main(int argc, char **argv)
         else if (a == "--high-freq") cfg.high_freq = (float)atof(val());
         else if (a == "--lift-coef") cfg.lift_coef = (float)atof(val());
         else if (a == "--c0") cfg.want_c0 = atoi(val()) != 0;
-        else if (a == "--alpha") cfg.alpha = (float)atof(val());
+        else if (a == "--alpha") { cfg.alpha = (float)atof(val()); if (cfg.alpha_max < cfg.alpha) cfg.alpha_max = cfg.alpha; }
+        else if (a == "--alpha-max") cfg.alpha_max = (float)atof(val());
+        else if (a == "--alpha-step") cfg.alpha_step = (float)atof(val());
+        else if (a == "--preemphasis") cfg.preemphasis = (float)atof(val());
         else if (a == "--norm") cfg.norm_type = atoi(val());
         else if (a == "--dyn") cfg.dyn_type = atoi(val());
         else if (a == "--l1") cfg.delta_l1 = atoi(val());
@@ -231,6 +255,7 @@ int main(int argc, char **argv)
                                                           cfg.delta_l2, cfg.norm_after_dyn, cfg.device));
             param->set_window(window.data());
             if (cfg.fix_flush) param->fix_flush_statics(true);
+            if (cfg.preemphasis > 0.f) param->set_preemphasis(cfg.preemphasis);
             process_file(param.get(), cfg, files[i], files[i + 1]);
         }
     } catch (const std::exception &e) {

@@ -32,7 +32,7 @@ public:
     {
         return (int)std::floor(float(samples - (m_window_size - m_shift)) / m_shift);
     }
-    virtual void set_alpha(float alpha) { m_alpha = alpha; } // virtual here so accelerator objects can forward it
+    void set_alpha(float alpha) { m_alpha = alpha; } // NOT virtual (parambase.h:25): objects read m_alpha in apply()
 
     virtual void set_window(const float *window) = 0;
     virtual int set_input(const short *data, int samples) = 0;

@@ -10,7 +10,11 @@
 #include <string>
 
 #include "afe_cuda.h"
+// Inside the reference's tree include its own "mfccbase.h" first and define AFE_USE_REFERENCE_HEADERS: the classes below
+// then derive from the reference's ParamBase / MfccBase (same names, same protected members) instead of the mirror.
+#ifndef AFE_USE_REFERENCE_HEADERS
 #include "afe_stage_api.hpp"
+#endif
 
 namespace afe_detail {
 inline void check(int rc)
@@ -40,7 +44,8 @@ public:
     MfccCuda(const MfccCuda &) = delete;
     MfccCuda &operator=(const MfccCuda &) = delete;
 
-    void set_alpha(float alpha) override { ParamBase::set_alpha(alpha); afe_detail::check(afe_mfcc_set_alpha(m_handle, alpha)); }
+    // ParamBase::set_alpha is not virtual and the driver calls it through a ParamBase* (parambase.h:25, ASR_OCL.cpp:241,276):
+    // like MfccCpu::filter (mfcccpu.cpp:194) this object reads the protected m_alpha when apply() runs.
     void set_window(const float *window) override { afe_detail::check(afe_mfcc_set_window(m_handle, window)); }
     int set_input(const short *data, int samples) override
     {
@@ -55,7 +60,11 @@ public:
         m_last_block = true;
         return frames;
     }
-    void apply() override { afe_detail::check(afe_mfcc_apply(m_handle)); }
+    void apply() override
+    {
+        afe_detail::check(afe_mfcc_set_alpha(m_handle, m_alpha));
+        afe_detail::check(afe_mfcc_apply(m_handle));
+    }
     void get_output_data(float *data_out, int window_count) override
     {
         afe_detail::check(afe_mfcc_get_output(m_handle, data_out, window_count));
@@ -63,6 +72,9 @@ public:
     // extensions: the reference object cannot be reused after flush() (m_last_block is never cleared, Q3)
     void reset() { afe_detail::check(afe_mfcc_reset(m_handle)); m_last_block = false; }
     void fix_flush_statics(bool on) { afe_detail::check(afe_mfcc_set_option(m_handle, AFE_OPT_FIX_FLUSH_STATICS, on)); }
+    // per-frame pre-emphasis before the window (the reference has none: 0 is its behaviour)
+    void set_preemphasis(float coefficient) { afe_detail::check(afe_mfcc_set_preemphasis(m_handle, coefficient)); }
+    bool uses_fused_kernel() const { return afe_mfcc_uses_fused_kernel(m_handle) != 0; }
 
 private:
     afe_mfcc *m_handle;
@@ -78,6 +90,7 @@ public:
     }
     void cleanup() { afe_segmenter_destroy(m_h); m_h = nullptr; }
     void set_window(const float *window) { afe_detail::check(afe_segmenter_set_window(m_h, window)); }
+    void set_preemphasis(float coefficient) { afe_detail::check(afe_segmenter_set_preemphasis(m_h, coefficient)); }
     // d_data_out: DEVICE float[window_count_no_delta][ceil2(window_size)]
     void set_input(const short *data_in, float *d_data_out, int samples, int &window_count, int &window_count_no_delta)
     {
@@ -125,6 +138,23 @@ public:
     {
         afe_detail::check(afe_normalizer_normalize(m_h, d_data, offset, window_count, use_last_stats ? 1 : 0));
     }
+    // Corpus-level CMVN (the exchange lives here): reset -> accumulate (every block / shard) -> allreduce (every rank) ->
+    // finalize -> apply (every block). The three kernels of NormalizerOpenCL::normalize (normalizeropencl.cpp:123-158) as
+    // separate verbs, the NCCL all-reduce of the record (sum | sumsq | count | min | max) between the first two.
+    void reset() { afe_detail::check(afe_normalizer_reset(m_h)); }
+    void accumulate(const float *d_data, int offset, int window_count)
+    {
+        afe_detail::check(afe_normalizer_accumulate(m_h, d_data, offset, window_count));
+    }
+    void allreduce(void *nccl_comm) { afe_detail::check(afe_normalizer_allreduce(m_h, nccl_comm)); }
+    void finalize() { afe_detail::check(afe_normalizer_finalize(m_h)); }
+    void apply(float *d_data, int offset, int window_count)
+    {
+        afe_detail::check(afe_normalizer_apply(m_h, d_data, offset, window_count));
+    }
+    int stats_len() const { return afe_normalizer_stats_len(m_h); }
+    void get_stats(double *h_stats) { afe_detail::check(afe_normalizer_get_stats(m_h, h_stats)); }
+    void set_stats(const double *h_stats) { afe_detail::check(afe_normalizer_set_stats(m_h, h_stats)); }
 
 private:
     afe_normalizer *m_h;

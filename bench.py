@@ -211,8 +211,7 @@ def run_b200(args):
 
     p = params_dict()
     ap = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in p.items() if k != "alpha"})
-    flags = (afe.BATCH_Q1_EXACT | (afe.BATCH_FAST_MATH if args.fast_math else 0) | (afe.BATCH_NO_TMA if args.no_tma else 0) |
-             (afe.BATCH_WS_KERNEL if args.ws_kernel else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0))
+    flags = (afe.BATCH_Q1_EXACT | (afe.BATCH_NO_TMA if args.no_tma else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0))
     # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -385,7 +384,7 @@ def run_b200(args):
                 "audio_hours_per_s": value * S / SR / 3600.0, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks, "corpus_cmvn": corpus,
                 "kernels_per_step": [b.kernel_name],
-                "tiles_per_gpu": b.num_tiles, "flags": {"fast_math": bool(args.fast_math), "tma": not args.no_tma}}
+                "tiles_per_gpu": b.num_tiles, "flags": {"tma": not args.no_tma, "devtools": bool(afe.lib().afe_build_flags() & 1)}}
         print(json.dumps(line), flush=True)
     b.close()
     if world > 1:
@@ -399,10 +398,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU (BASELINE config 3: 10000)")
-    ap.add_argument("--fast-math", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to their GPU's NUMA node (A/B, N > 1)")
     ap.add_argument("--no-cluster", action="store_true", help="ticket-scheme normalisation instead of clusters + DSMEM (A/B)")
-    ap.add_argument("--ws-kernel", action="store_true", help="the warp-specialised persistent k_fused_ws instead of k_fused_mfcc (A/B)")
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

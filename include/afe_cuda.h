@@ -20,7 +20,10 @@
 extern "C" {
 #endif
 
-#define AFE_ABI_VERSION 1
+/* 2: Normalizer-owned corpus verbs (afe_normalizer_accumulate / allreduce / finalize / apply; afe_normalizer_allreduce now takes
+ *    the Normalizer, afe_batch_normalizer() hands out the batch's), pre-emphasis setters, afe_build_flags, the streaming
+ *    object runs on the fused kernel, AFE_BATCH_WS_KERNEL / AFE_BATCH_FAST_MATH removed. */
+#define AFE_ABI_VERSION 2
 
 /* normalizer.h:5 */
 enum afe_norm { AFE_NORM_NONE = 0, AFE_NORM_CMN = 1, AFE_NORM_CVN = 2, AFE_NORM_MINMAX = 3 };
@@ -48,6 +51,8 @@ typedef struct afe_params {
 
 const char *afe_last_error(void);
 int afe_abi_version(void);
+/* bit 0: built with -DAFE_DEVTOOLS (timing hooks read from the environment; never in a product build) */
+int afe_build_flags(void);
 /* number of visible CUDA devices; 0 with an error string when the driver/runtime is unusable */
 int afe_device_count(void);
 
@@ -81,6 +86,9 @@ int afe_mfcc_create(const afe_params *p, int cuda_device, afe_mfcc **out);      
 void afe_mfcc_destroy(afe_mfcc *h);                                               /* ~MfccOpenCL */
 int afe_mfcc_set_window(afe_mfcc *h, const float *window);                        /* ParamBase::set_window */
 int afe_mfcc_set_alpha(afe_mfcc *h, float alpha);                                 /* ParamBase::set_alpha (VTLN) */
+/* Per-frame pre-emphasis before the window: y[j] = x[j] - c*x[j-1], y[0] = (1-c)*x[0]. The reference has none
+ * (segmentercpu.cpp:21-27): the default 0 is its behaviour, bit for bit. 0 <= c < 1. */
+int afe_mfcc_set_preemphasis(afe_mfcc *h, float coefficient);
 int afe_mfcc_input_buffer_size(const afe_mfcc *h);                                /* ParamBase::get_input_buffer_size */
 int afe_mfcc_estimated_window_count(const afe_mfcc *h, int samples);              /* ParamBase::estimated_window_count */
 int afe_mfcc_output_width(const afe_mfcc *h);                                     /* get_output_data_width */
@@ -94,8 +102,15 @@ int afe_mfcc_apply(afe_mfcc *h);                                                
 int afe_mfcc_get_output(afe_mfcc *h, float *out, int frames);
 /* The reference never clears m_last_block (Q3): one object per utterance. reset() makes the handle reusable. */
 int afe_mfcc_reset(afe_mfcc *h);
-enum afe_mfcc_option { AFE_OPT_FIX_FLUSH_STATICS = 1 };
+enum afe_mfcc_option {
+    AFE_OPT_FIX_FLUSH_STATICS = 1,
+    AFE_OPT_STAGED_KERNELS = 2     /* A-B test: one kernel per reference stage instead of the fused kernel; before set_window */
+};
 int afe_mfcc_set_option(afe_mfcc *h, int option, int value);
+/* 1 when the object's blocks run through the fused kernel (one launch per apply()), 0 when the parameter set needs the
+ * staged kernels (FFT sizes other than 256/512, odd shift, normalisation before the deltas, ...). Both run on the GPU. */
+int afe_mfcc_uses_fused_kernel(const afe_mfcc *h);
+int afe_mfcc_kernel_launches(const afe_mfcc *h); /* fused-kernel launches since creation */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Stage objects with device buffers (the `cl_mem` arguments of the OpenCL variants become device pointers).
@@ -105,6 +120,7 @@ int afe_segmenter_create(int window_size, int shift, int window_limit, int delta
                          afe_segmenter **out);                                    /* ::init */
 void afe_segmenter_destroy(afe_segmenter *s);                                     /* ::cleanup */
 int afe_segmenter_set_window(afe_segmenter *s, const float *window);
+int afe_segmenter_set_preemphasis(afe_segmenter *s, float coefficient);           /* see afe_mfcc_set_preemphasis */
 /* d_out: DEVICE float[window_count_no_delta][ceil2(W)], zero padded beyond W */
 int afe_segmenter_set_input(afe_segmenter *s, const int16_t *data_in, float *d_out, int samples,
                             int *window_count, int *window_count_no_delta);
@@ -126,6 +142,20 @@ int afe_normalizer_create(int norm_type, int dim, int cuda_device, afe_normalize
 void afe_normalizer_destroy(afe_normalizer *n);
 /* in place on DEVICE float[window_count][dim] starting `offset` floats into d_data; stats in double */
 int afe_normalizer_normalize(afe_normalizer *n, float *d_data, int offset, int window_count, int use_last_stats);
+/* Corpus-level CMVN: the three kernels of NormalizerOpenCL::normalize (norm.cl kernelSum :1-40, kernelFinalizeSum :42-78,
+ * kernelNormalize :80-125; normalizeropencl.cpp:123-158) as separate verbs on the Normalizer's running record, with the
+ * ONE collective of the path between the first two. Record = sum[dim] | sumsq[dim] | count | min[dim] | max[dim] doubles.
+ *   reset -> accumulate (any number of blocks / shards) -> allreduce (all ranks) -> finalize -> apply (any number of blocks) */
+int afe_normalizer_stats_len(const afe_normalizer *n);                            /* 4*dim + 1 */
+int afe_normalizer_reset(afe_normalizer *n);
+int afe_normalizer_accumulate(afe_normalizer *n, const float *d_data, int offset, int window_count);
+/* in-place NCCL all-reduce of the record over the communicator's ranks (ncclComm_t as void*): sums and count with ncclSum,
+ * minima with ncclMin, maxima with ncclMax, one NCCL group; asynchronous on the Normalizer's stream */
+int afe_normalizer_allreduce(afe_normalizer *n, void *nccl_comm);
+int afe_normalizer_finalize(afe_normalizer *n);                                   /* normalizercpu.cpp:31-66 on the record */
+int afe_normalizer_apply(afe_normalizer *n, float *d_data, int offset, int window_count);
+int afe_normalizer_get_stats(afe_normalizer *n, double *h_stats);                 /* HOST double[stats_len] */
+int afe_normalizer_set_stats(afe_normalizer *n, const double *h_stats);           /* e.g. sums reduced by another transport */
 
 /* small helpers so stage objects can be driven from C / ctypes without another CUDA binding */
 int afe_device_malloc(int cuda_device, size_t bytes, void **d_ptr);
@@ -150,20 +180,16 @@ enum afe_stats_scope {
 enum afe_batch_flags {
     AFE_BATCH_Q1_EXACT = 1,        /* reproduce the single-block flush quirk Q1 (statics of the last D rows) */
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
-    AFE_BATCH_FAST_MATH = 4,       /* MUFU log2 approximation in the fused kernel (tolerance-checked in tests) */
     AFE_BATCH_UNFUSED_NORM = 8,    /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
-    AFE_BATCH_NO_CLUSTER = 32,     /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
+    AFE_BATCH_NO_CLUSTER = 32      /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
                                       place via L2) instead of thread-block clusters + distributed shared memory (A-B test) */
-    AFE_BATCH_WS_KERNEL = 16       /* run the warp-specialised persistent kernel k_fused_ws (producer warps FFT, consumer warps
-                                      mel/DCT/deltas; whole utterances per tile) when the regression is the reference's
-                                      default (static + delta + delta-delta, l1 = l2 = 3). Measured 1.6 % slower than
-                                      k_fused_mfcc at BASELINE config 3 (profiles/r01_ws_vs_generic.txt): opt-in. */
 };
 
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out);
 void afe_batch_destroy(afe_batch *b);
 int afe_batch_set_window(afe_batch *b, const float *window);
 int afe_batch_set_alpha(afe_batch *b, float alpha);
+int afe_batch_set_preemphasis(afe_batch *b, float coefficient);                   /* see afe_mfcc_set_preemphasis */
 int afe_batch_set_options(afe_batch *b, int stats_scope, int flags);
 /* Use the caller's CUDA stream (cudaStream_t / CUstream as void*); NULL -> the handle's own stream. */
 int afe_batch_set_stream(afe_batch *b, void *cuda_stream);
@@ -176,7 +202,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *sample_offsets, const int64_t *s
 int afe_batch_frame_offsets(const afe_batch *b, int64_t *frame_offsets);
 int afe_batch_num_tiles(const afe_batch *b);
 int afe_batch_kernel_launches(const afe_batch *b); /* kernels launched by the last run */
-const char *afe_batch_kernel_name(const afe_batch *b); /* fused kernel the current plan runs: "k_fused_ws" | "k_fused_mfcc" */
+const char *afe_batch_kernel_name(const afe_batch *b); /* "k_fused_mfcc" */
 /* d_pcm: DEVICE int16 buffer covering every [offset, offset+length) (+16 B slack after the last sample),
  * d_out: DEVICE float[total_frames][width]. Asynchronous on the handle's stream. */
 int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out);
@@ -184,8 +210,10 @@ int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out);
 int afe_batch_extract_device(afe_batch *b, const int16_t *d_pcm, float *d_out);
 /* ... reduce them to corpus sums on the device (DEVICE double[stats_len], record layout at afe_cmvn_finalize_host) ... */
 int afe_batch_corpus_stats(afe_batch *b, double **d_stats, int *stats_len);
-/* ... all-reduce over the ranks of an NCCL communicator (ncclComm_t as void*) — the ONE collective of the path ... */
-int afe_normalizer_allreduce(afe_batch *b, void *nccl_comm);
+/* ... which live in the batch's corpus Normalizer (NULL unless the scope is AFE_STATS_CORPUS and norm != NONE; owned by the
+ * batch, valid until the next afe_batch_plan / destroy): all-reduce them over the ranks with
+ * afe_normalizer_allreduce(afe_batch_normalizer(b), comm) — the ONE collective of the path ... */
+afe_normalizer *afe_batch_normalizer(afe_batch *b);
 /* ... or merge externally reduced sums (HOST double[stats_len]), e.g. from a gloo all-reduce in CPU tests ... */
 int afe_batch_set_corpus_stats(afe_batch *b, const double *h_stats, int stats_len);
 /* ... then finalise mean / scale and normalise d_out in place. */

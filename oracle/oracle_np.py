@@ -63,7 +63,11 @@ def mfcc(pcm, p, q1=False, stats_rows=None):
     w = make_window(W).astype(np.float32).astype(np.float64)
     idx = np.arange(T)[:, None] * S + np.arange(W)[None, :]
     fr = np.zeros((T, N2))
-    fr[:, :W] = pcm.astype(np.float64)[idx] * w
+    x = pcm.astype(np.float64)[idx]
+    pre = p.get("preemphasis", 0.0)   # NOT in the reference (segmentercpu.cpp:21-27 has none): the new path's optional
+    if pre:                           # per-frame pre-emphasis y[j] = x[j] - pre*x[j-1], y[0] = (1-pre)*x[0]
+        x = x - pre * np.concatenate([x[:, :1], x[:, :-1]], axis=1)
+    fr[:, :W] = x * w
     mag = np.abs(np.fft.rfft(fr, axis=1)) / N2
     _, edge, Wm = mel_tables(nb, N2, p["sample_rate"], p["low_freq"], p["high_freq"], p.get("alpha", 1.0))
     E = np.log(np.maximum(mag @ Wm.T, 1e-30))

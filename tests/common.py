@@ -65,3 +65,28 @@ def run_batch(p, utts, stats_scope=0, flags=0, alpha=None, host=True):
         return [out[fo[i]:fo[i + 1]] for i in range(len(utts))]
     finally:
         b.close()
+
+
+def ref_alpha_sweep(oracle, pcm, p, limit, alphas):
+    """The reference driver's VTLN sweep (ASR_OCL.cpp:227-301) on the reference's own objects: per block ONE set_input, then
+    set_alpha -> apply -> get_output_data per alpha (so the flush block is normalised with the LAST alpha's statistics).
+    -> list of [T, width] arrays, one per alpha."""
+    ref = ol.RefMfcc(oracle, limit, p)
+    ref.set_window(oracle.window(p["window_size"]))
+    n = ref.get_input_buffer_size()
+    rows = [[] for _ in alphas]
+
+    def emit(wc):
+        for k, a in enumerate(alphas):
+            ref.set_alpha(a)
+            ref.apply()
+            rows[k].append(ref.get_output_data(wc))
+    for pos in range(0, len(pcm), n):
+        wc = ref.set_input(pcm[pos:pos + n])
+        if wc > 0:
+            emit(wc)
+    wc = ref.flush()
+    if wc > 0:
+        emit(wc)
+    ref.close()
+    return [np.concatenate(r) for r in rows]

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from common import assert_close
+from common import assert_close, ref_alpha_sweep
 from golden_io import load_pcm
 
 pytestmark = pytest.mark.gpu
@@ -115,3 +115,51 @@ def test_batch_mode_text_equals_streaming_layout(tmp_path):
     b, s = open(tmp_path / "b.txt").read().splitlines(), open(tmp_path / "s.txt").read().splitlines()
     assert len(b) == len(s) == 504
     assert [l.split(" | ")[0] for l in b] == [l.split(" | ")[0] for l in s]   # timestamps (Q6) byte for byte
+
+
+def test_alpha_sweep_through_parambase_pointer(oracle, tmp_path):
+    """VTLN sweep of the reference driver (ASR_OCL.cpp:198-218,234-243): one set_input, then set_alpha -> apply ->
+    get_output_data per alpha through a ParamBase* whose set_alpha is NOT virtual (parambase.h:25); one output file per
+    alpha, named like the reference names them. A sweep whose alphas did not reach the device would write identical files."""
+    pcm = load_pcm()["sample1"]
+    wav = str(tmp_path / "s.wav")
+    write_wav(wav, pcm)
+    run(["--banks", "23", "--norm", "1", "--dyn", "2", "--text-output", "0", "--alpha", "0.9", "--alpha-max", "1.1",
+         "--alpha-step", "0.1", wav, str(tmp_path / "o.bin")])
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("o") and f.endswith(".bin"))
+    assert files == ["o0.900000.bin", "o1.000000.bin", "o1.100000.bin"], files
+    p = ol.default_params(norm="cmn", dyn="acc")
+    alphas = [np.float32(0.9) + i * np.float32(0.1) for i in range(3)]   # float arithmetic of the driver's loop
+    want = ref_alpha_sweep(oracle, pcm, p, 10_000_000, alphas)
+    outs = []
+    for k, f in enumerate(files):
+        got = np.fromfile(str(tmp_path / f), np.float32).reshape(-1, 39)
+        assert_close(got, want[k], p, f"alpha {alphas[k]}")
+        outs.append(got)
+    assert np.abs(outs[0] - outs[1]).max() > 0.1 and np.abs(outs[2] - outs[1]).max() > 0.1
+
+
+DROPIN = os.path.join(ol.ROOT, "oracle", "_ref", "dropin_ref")
+
+
+def test_dropin_with_the_reference_base_classes(oracle, tmp_path):
+    """oracle/_ref/dropin_ref = tests/cpp/dropin_main.cpp compiled against the REFERENCE's parambase.h / mfccbase.h and
+    linked with the reference's parambase.cpp / mfccbase.cpp (oracle/Makefile) + MfccCuda over libafe_cuda.so: the object
+    drops into the reference's own class hierarchy, and the alpha set through the non-virtual ParamBase::set_alpha reaches
+    the GPU (streamed in 16 000-sample blocks, CMN, delta + delta-delta)."""
+    if not os.path.exists(DROPIN):
+        pytest.skip("oracle/_ref/dropin_ref not built (needs the reference tree at build time)")
+    pcm = load_pcm()["a1"]
+    raw, out = str(tmp_path / "a1.s16"), str(tmp_path / "a1.f32")
+    np.ascontiguousarray(pcm, "<i2").tofile(raw)
+    r = subprocess.run([DROPIN, raw, out, "16000", "0.9", "1.1", "0.1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(out, np.float32).reshape(3, 504, 39)
+    # the reference objects fed the same blocks and the same sweep (statistics of the flush block = the LAST alpha's)
+    p = ol.default_params(norm="cmn", dyn="acc")
+    alphas = [np.float32(0.9) + np.float32(0.1) * i for i in range(3)]
+    want = ref_alpha_sweep(oracle, pcm, p, 16000, alphas)
+    for k in range(3):
+        assert_close(got[k], want[k], p, f"dropin alpha {alphas[k]}")
+    assert np.abs(got[0] - got[1]).max() > 0.1

@@ -118,3 +118,27 @@ def test_afe_extract_command_line_errors(tmp_path):
     assert r.returncode == 2 and "can't open list" in r.stderr
     r = subprocess.run([exe, "only_one_file.wav"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 2
+
+
+def test_mfcccuda_compiles_against_the_reference_headers():
+    """Drop-in at source level: MfccCuda derives from the REFERENCE's own MfccBase (parambase.h:25: set_alpha is not virtual)
+    when built with -DAFE_USE_REFERENCE_HEADERS, and is driven through a ParamBase* (tests/cpp/dropin_check.cpp).
+    Only where the reference tree exists (the authoring container); the GPU tier runs the linked binary."""
+    import subprocess
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("no reference tree")
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-DAFE_USE_REFERENCE_HEADERS", "-I/root/reference",
+                        "-I" + os.path.join(ol.ROOT, "include"), "-I" + os.path.join(ol.ROOT, "asr-featext-opencl_b200", "host"),
+                        os.path.join(ol.ROOT, "tests", "cpp", "dropin_check.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    assert r.returncode == 0, r.stdout
+    mirror = open(os.path.join(ol.ROOT, "asr-featext-opencl_b200", "host", "afe_stage_api.hpp")).read()
+    assert "virtual void set_alpha" not in mirror and "void set_alpha(float alpha) { m_alpha = alpha; }" in mirror
+
+
+def test_numpy_oracle_preemphasis_zero_is_identity():
+    pcm = (np.random.default_rng(0).standard_normal(8000) * 3000).astype(np.int16)
+    p = ol.default_params(dyn="acc")
+    a, b = oracle_np.mfcc(pcm, p), oracle_np.mfcc(pcm, dict(p, preemphasis=0.0))
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(oracle_np.mfcc(pcm, dict(p, preemphasis=0.97)) - a).max() > 0.1
