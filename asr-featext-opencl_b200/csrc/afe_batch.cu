@@ -156,26 +156,26 @@ void count_launch(int n) { g_launches.fetch_add(n); }
 
 // ------------------------------------------------------------------------------------------------ K1 launch table
 #define AFE_DECL_INST(k) cudaError_t fused_launch_##k(const FusedLaunch &); int fused_max_clusters_##k(const FusedLaunch &);
-AFE_DECL_INST(0) AFE_DECL_INST(1) AFE_DECL_INST(2) AFE_DECL_INST(3) AFE_DECL_INST(4) AFE_DECL_INST(5)
-AFE_DECL_INST(6) AFE_DECL_INST(7) AFE_DECL_INST(8) AFE_DECL_INST(9) AFE_DECL_INST(10) AFE_DECL_INST(11)
+#define AFE_FOR_EACH_INST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) \
+    X(18) X(19) X(20) X(21) X(22) X(23)
+AFE_FOR_EACH_INST(AFE_DECL_INST)
 #undef AFE_DECL_INST
 
 cudaError_t launch_fused_variant(int key, const FusedLaunch &fl)
 {
     typedef cudaError_t (*fn_t)(const FusedLaunch &);
-    static const fn_t table[kFusedVariants] = {fused_launch_0, fused_launch_1, fused_launch_2,  fused_launch_3,
-                                               fused_launch_4, fused_launch_5, fused_launch_6,  fused_launch_7,
-                                               fused_launch_8, fused_launch_9, fused_launch_10, fused_launch_11};
+#define AFE_ENTRY(k) fused_launch_##k,
+    static const fn_t table[kFusedVariants] = {AFE_FOR_EACH_INST(AFE_ENTRY)};
+#undef AFE_ENTRY
     if (key < 0 || key >= kFusedVariants) return cudaErrorInvalidValue;
     return table[key](fl);
 }
 int fused_variant_max_clusters(int key, const FusedLaunch &fl)
 {
     typedef int (*fn_t)(const FusedLaunch &);
-    static const fn_t table[kFusedVariants] = {fused_max_clusters_0, fused_max_clusters_1, fused_max_clusters_2,
-                                               fused_max_clusters_3, fused_max_clusters_4, fused_max_clusters_5,
-                                               fused_max_clusters_6, fused_max_clusters_7, fused_max_clusters_8,
-                                               fused_max_clusters_9, fused_max_clusters_10, fused_max_clusters_11};
+#define AFE_ENTRY(k) fused_max_clusters_##k,
+    static const fn_t table[kFusedVariants] = {AFE_FOR_EACH_INST(AFE_ENTRY)};
+#undef AFE_ENTRY
     if (key < 0 || key >= kFusedVariants) return -1;
     return table[key](fl);
 }
@@ -310,7 +310,7 @@ bool FusedEngine::cluster_schedulable(int cluster, const FusedArgs &a, cudaStrea
     if (cluster < 1 || cluster > 4) return false;
     if (cluster_probe[cluster] < 0) {
         FusedLaunch fl{a, L, &mc, cluster, cluster, st};
-        const int n = fused_variant_max_clusters(key, fl);
+        const int n = fused_variant_max_clusters(key, fl); // same footprint with and without pre-emphasis
         cluster_probe[cluster] = n > 0 ? n : 0;
     }
     return cluster_probe[cluster] > 0;
@@ -320,7 +320,7 @@ void FusedEngine::launch(const FusedArgs &a, int grid, int cluster, cudaStream_t
 {
     if (!window_set) throw Error("set_window must be called before running");
     FusedLaunch fl{a, L, &mc, grid, cluster, st};
-    const cudaError_t e = launch_fused_variant(key, fl);
+    const cudaError_t e = launch_fused_variant(key + (a.pre != 0.f ? 12 : 0), fl);
     if (e != cudaSuccess) {
         cudaGetLastError();
         throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at k_fused_mfcc launch" + (cluster > 0 ? " (clustered)" : ""));

@@ -166,14 +166,15 @@ template <bool FAST> __device__ __forceinline__ float mag_sqrt(float x)
 //   mag_out  : BINS floats (always written; padding frames point at a row nobody reads)
 //   SCALED   : true -> |X|/N2 (reference value); false -> |2X| (= 2*N2 times that; the caller folds the exact
 //              power-of-two factor 0.5/N2 into its mel weights)
-template <int N2, int NZ, bool FAST, bool SCALED = true>
+//   PRE      : compile the pre-emphasis variant of the load (taken when pre != 0); false keeps the reference path free of it
+template <int N2, int NZ, bool FAST, bool SCALED = true, bool PRE = true>
 __device__ __forceinline__ void fft_frame_mag(const uint32_t *words, const LaneConsts<N2, NZ> &lc, float2 *scratch,
                                               float *mag_out, int lf, float pre = 0.f)
 {
     using C = FftCfg<N2>;
     constexpr int M = C::M, R = C::R, RS = C::RS;
     float2 x[16];
-    if (pre == 0.f) { // warp-uniform: the reference has no pre-emphasis (segmentercpu.cpp:21-27), this is its path
+    if (!PRE || pre == 0.f) { // the reference has no pre-emphasis (segmentercpu.cpp:21-27), this is its path
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) {
             if (n1 < NZ) {

@@ -404,7 +404,7 @@ __device__ __forceinline__ void normalise_role(const FusedArgs &a, const Tile tl
 
 // KF = filters per warp in phase 2 (ceil(num_banks / WARPS), rounded up to 3, 5 or 8): the phase is unrolled KF times,
 // so a tight bound keeps the round loop inside the instruction cache.
-template <int N2, int NZ, int kFusedWarps, int KF>
+template <int N2, int NZ, int kFusedWarps, int KF, bool PRE>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
@@ -505,7 +505,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 const int fl = it * FPW + fw;                    // frame within the warp's 8 (adjacent frames per call)
                 const int fr = warp * kWarpFrames + fl;          // frame within the round
                 const uint32_t *words = reinterpret_cast<const uint32_t *>(w_pcm) + ((fl * a.S) >> 1);
-                dev::fft_frame_mag<N2, NZ, true, false>(words, lc, w_scratch + fw * SCR, s_mags + mag_row(fr) * kMagStride, lf, a.pre);
+                dev::fft_frame_mag<N2, NZ, true, false, PRE>(words, lc, w_scratch + fw * SCR, s_mags + mag_row(fr) * kMagStride, lf, a.pre);
             }
             // the staging buffer is free again: prefetch this warp's next round while phase 2 runs
             if (a.use_tma && lane == 0 && r + 1 < nrounds) issue_tma(r + 1);
@@ -773,7 +773,12 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 dst[0] = s0; dst[1] = s1; dst[2] = lo; dst[3] = hi;
             }
         }
-
+        if (a.use_last) {
+            // flush block of the streaming object, generic regression: the rows just written are normalised in place with
+            // the previous block's statistics (mfcccpu.cpp:389)
+            __syncthreads();
+            dev::normalise_tile_rows(a.out, tl, width, a.norm_type, a.g_mean, a.g_scale, reinterpret_cast<float *>(smem + L.off_dhat));
+        }
     }
 
     // ---- fused normalisation (per-utterance statistics scopes): the LAST tile of an utterance to finish reduces the

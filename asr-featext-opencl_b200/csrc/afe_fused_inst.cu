@@ -1,15 +1,16 @@
-// One instantiation of the fused kernel per translation unit: nvcc -DAFE_INST_KEY=<0..11> (see the Makefile).
+// One instantiation of the fused kernel per translation unit: nvcc -DAFE_INST_KEY=<0..23> (see the Makefile).
 #include "afe_internal.h"
 #include "afe_fused_launch.h"
 
 #ifndef AFE_INST_KEY
-#error "compile with -DAFE_INST_KEY=0..11"
+#error "compile with -DAFE_INST_KEY=0..23"
 #endif
 
 namespace afe {
 
 namespace {
-constexpr int kKey = AFE_INST_KEY;
+constexpr int kKey = AFE_INST_KEY % 12;
+constexpr bool kPre = AFE_INST_KEY >= 12;   // keys 12..23: the same shapes with per-frame pre-emphasis in the load
 constexpr int kN2 = kKey < 6 ? 512 : 256;
 constexpr int kNZ = (kKey % 6) < 3 ? 13 : 16;
 constexpr int kKF = (kKey % 3) == 0 ? 3 : (kKey % 3) == 1 ? 5 : 8;
@@ -29,7 +30,7 @@ void fill(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &attr, const FusedLaunch 
 
 cudaError_t AFE_CAT(fused_launch_, AFE_INST_KEY)(const FusedLaunch &fl)
 {
-    auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF>;
+    auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF, kPre>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.L.total);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
@@ -39,7 +40,7 @@ cudaError_t AFE_CAT(fused_launch_, AFE_INST_KEY)(const FusedLaunch &fl)
 
 int AFE_CAT(fused_max_clusters_, AFE_INST_KEY)(const FusedLaunch &fl)
 {
-    auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF>;
+    auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF, kPre>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.L.total) != cudaSuccess) return -1;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
     fill(cfg, attr, fl);
