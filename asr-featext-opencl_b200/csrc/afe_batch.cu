@@ -91,15 +91,13 @@ void upload_window(const Derived &d, const float *window, MelTables &t, cudaStre
 __global__ void k_reduce_partials(const double *__restrict__ partials, const int *__restrict__ tile_begin,
                                   const double *__restrict__ counts, int width, double *__restrict__ stats)
 {
+    // the canonical summation order of dev::group_total, so that K2 and the in-kernel schemes agree bit for bit
+    extern __shared__ double s_seg[];
     const int g = blockIdx.x, c = threadIdx.x;
+    double s0, s1, lo, hi;
+    dev::group_total(partials, width, tile_begin[g], tile_begin[g + 1] - tile_begin[g], threadIdx.x, blockDim.x, s_seg,
+                     c < width ? c : 0, s0, s1, lo, hi);
     if (c >= width) return;
-    double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
-#pragma unroll 8
-    for (int t = tile_begin[g]; t < tile_begin[g + 1]; t++) { // fixed order: deterministic (loads are hoisted, adds stay ordered)
-        const double *p = partials + ((long long)t * width + c) * 4;
-        s0 += p[0]; s1 += p[1];
-        lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
-    }
     double *o = stats + (long long)g * (4 * width + 1);
     o[c] = s0; o[width + c] = s1; o[2 * width + 1 + c] = lo; o[3 * width + 1 + c] = hi;
     if (c == 0) o[2 * width] = counts[g];
@@ -255,12 +253,20 @@ void FusedEngine::ensure_mel(float alpha)
     if (mc_alpha != alpha) { build_mel_const(d, alpha, mc); mc_alpha = alpha; }
 }
 
-int FusedEngine::plan_rows(std::vector<Tile> &tiles, long long pcm_off, long long out_row0, int T, int t_first, int n_out,
-                           int group) const
+int FusedEngine::latency_tile(int n_out) const
 {
-    if (n_out <= 0) return 0;
+    const int target = std::max(1, 2 * sm_count);
+    const int want = (n_out + target - 1) / target;                          // rows per tile for ~2 tiles per SM
+    const int rounds = std::max(2, (want + 2 * d.D + kRoundFrames - 1) / kRoundFrames);
+    return std::max(1, std::min(nout_max, rounds * kRoundFrames - 2 * d.D));
+}
+
+void FusedEngine::plan_uniform(int T, int t_first, int n_out, int nout_cap, int &ntile, int &nout) const
+{
+    const int cap = nout_cap > 0 ? std::min(nout_cap, nout_max) : nout_max;
     // number of tiles: fewest 32-frame rounds (the halo of D frames per side is recomputed by every tile)
-    int ntile = (n_out + nout_max - 1) / nout_max, best_cost = 1 << 30;
+    int best_cost = 1 << 30;
+    ntile = (n_out + cap - 1) / cap;
     for (int cand = ntile; cand <= ntile + 3; cand++) {
         const int no = (n_out + cand - 1) / cand;
         int cost = 0;
@@ -270,12 +276,22 @@ int FusedEngine::plan_rows(std::vector<Tile> &tiles, long long pcm_off, long lon
         }
         if (cost < best_cost) { best_cost = cost; ntile = cand; }
     }
-    const int nout = (n_out + ntile - 1) / ntile, first = (int)tiles.size(), count = (n_out + nout - 1) / nout;
+    nout = (n_out + ntile - 1) / ntile;
+    ntile = (n_out + nout - 1) / nout;
+}
+
+int FusedEngine::plan_rows(std::vector<Tile> &tiles, long long pcm_off, long long out_row0, int T, int t_first, int n_out,
+                           int group, int nout_cap) const
+{
+    if (n_out <= 0) return 0;
+    int count, nout;
+    plan_uniform(T, t_first, n_out, nout_cap, count, nout);
+    const int first = (int)tiles.size();
     for (int t0 = t_first; t0 < t_first + n_out; t0 += nout) {
         Tile tl;
         tl.pcm_off = pcm_off; tl.out_row0 = out_row0; tl.T = T; tl.t0 = t0;
         tl.nout = std::min(nout, t_first + n_out - t0); tl.group = group;
-        tl.tile0 = first; tl.ntiles = count;
+        tl.tile0 = first; tl.ntiles = count; tl.flags = 0; tl.pad_ = 0;
         tiles.push_back(tl);
     }
     return count;
@@ -425,7 +441,7 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
         a.counters = b->d_counters; a.work_counter = b->d_counters + b->n_groups;
         a.flags = b->d_flags; a.epoch = ++b->epoch; a.ntiles_launch = t1 - t0;
         a.g_mean = b->d_mean; a.g_scale = b->d_scale;
-        launch(a, 2 * (t1 - t0), 0);
+        launch(a, (t1 - t0) + std::min(t1 - t0, 2 * eng.sm_count), 0); // + one wave of normaliser roles
         return;
     }
     const bool cluster_ok = !(b->flags & AFE_BATCH_NO_CLUSTER) && d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
@@ -471,13 +487,13 @@ static void run_reduce(afe_batch *b, int g0 = 0, int g1 = -1)
     if (b->scope == AFE_STATS_CORPUS && b->n_tiles > 2 * b->corpus_blocks) {
         k_reduce_partials_level1<<<b->corpus_blocks, 128, 0, b->stream>>>(b->d_partials, b->n_tiles, w, b->d_scratch);
         AFE_CUDA(cudaGetLastError());
-        k_reduce_partials<<<1, 128, 0, b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, w, b->d_stats);
+        k_reduce_partials<<<1, 256, dev::kSegs * w * 4 * sizeof(double), b->stream>>>(b->d_scratch, b->d_scratch_begin, b->d_counts, w, b->d_stats);
         AFE_CUDA(cudaGetLastError());
         count_launch(2); b->last_launches += 2;
         return;
     }
-    k_reduce_partials<<<g1 - g0, 128, 0, b->stream>>>(b->d_partials, b->d_tile_begin + g0, b->d_counts + g0, w,
-                                                       b->d_stats + (size_t)g0 * (4 * w + 1));
+    k_reduce_partials<<<g1 - g0, 256, dev::kSegs * w * 4 * sizeof(double), b->stream>>>(b->d_partials, b->d_tile_begin + g0, b->d_counts + g0, w,
+                                                                                       b->d_stats + (size_t)g0 * (4 * w + 1));
     AFE_CUDA(cudaGetLastError());
     count_launch(); b->last_launches++;
 }

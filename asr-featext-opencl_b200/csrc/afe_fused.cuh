@@ -42,7 +42,11 @@ struct Tile {
     int group;           // statistics group (utterance index, or 0 for corpus scope)
     int tile0;           // index of the utterance's first tile
     int ntiles;          // tiles of the utterance
+    int flags;           // kTileNoStats | kTileQ1All
+    int pad_;
 };
+constexpr int kTileNoStats = 1; // the tile's rows do not enter the group's statistics (speculative flush rows of a stream block)
+constexpr int kTileQ1All = 2;   // every row of the tile takes its static D rows early (FusedArgs::q1 == 2 for this tile only)
 
 constexpr int kMaxBanks = 64;
 constexpr int kMaxWl4 = (2 * 257 + 10 * kMaxBanks + 3) / 4; // every bin feeds a rising and a falling side; lists start on a
@@ -95,6 +99,10 @@ struct FusedArgs {
     unsigned epoch;
     int ntiles_launch;
     float pre;           // pre-emphasis coefficient applied per frame before the window (0: none, the reference's behaviour)
+    // A block of the streaming object needs no tile table in memory: blk_ntiles > 0 describes its tiles (all of blk_nout
+    // output frames, the last one shorter) and, with blk_spec, one more tile holding the D rows a flush() right after this
+    // block would return (right edge replicated, no statistics): see dev::load_tile.
+    int blk_ntiles, blk_T, blk_t_first, blk_n_out, blk_nout, blk_spec, blk_spec_q1;
     int stats_kind;      // 0: none, 1: sums (CMN), 2: + sums of squares (CVN), 3: + min/max (MINMAX)
     int tc_max;          // capacity (frames) of the cepstra tile
     float rden1, rden2;  // 1 / (2*sum(l^2))
@@ -276,7 +284,8 @@ __device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, co
     const int cols = a.cols, width = a.width, T = tl.T, t0 = tl.t0, nout = tl.nout;
     const int rp = nthreads / cols, g = tid / cols, c = tid - g * cols;
     if (g >= rp) return;
-    const int rq = a.q1 ? (a.q1 == 2 ? 0 : max(0, T - 6 - t0)) : nout; // first row written with the static of 6 rows earlier (Q1)
+    const int q1 = (tl.flags & kTileQ1All) ? 2 : a.q1;
+    const int rq = q1 ? (q1 == 2 ? 0 : max(0, T - 6 - t0)) : nout; // first row written with the static of 6 rows earlier (Q1)
     const float rden1 = a.rden1, rden2 = a.rden2;
     double sum[3] = {0.0, 0.0, 0.0}, sumsq[3] = {0.0, 0.0, 0.0};
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -341,6 +350,73 @@ __device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, co
 } // namespace dev
 
 namespace dev {
+__device__ __forceinline__ Tile load_tile(const FusedArgs &a, int idx)
+{
+    if (a.blk_ntiles == 0) return a.tiles[idx];
+    const int D = a.l1 + a.l2;
+    Tile tl;
+    tl.pcm_off = 0; tl.out_row0 = -(long long)a.blk_t_first; tl.T = a.blk_T; tl.group = 0; tl.tile0 = 0;
+    tl.ntiles = a.blk_ntiles + a.blk_spec; tl.pad_ = 0;
+    if (idx < a.blk_ntiles) {
+        tl.t0 = a.blk_t_first + idx * a.blk_nout;
+        tl.nout = min(a.blk_nout, a.blk_t_first + a.blk_n_out - tl.t0);
+        tl.flags = 0;
+    } else { // rows [T - D, T): what flush() would return if the stream ended with this block (mfcccpu.cpp:373-390)
+        tl.t0 = a.blk_T - D; tl.nout = D;
+        tl.flags = kTileNoStats | (a.blk_spec_q1 ? kTileQ1All : 0);
+    }
+    return tl;
+}
+
+// Canonical order in which the per-tile statistics records of one group are summed (every scheme - cluster, ticket, role
+// scheme, K2 - must produce the same bits): up to kSeqTiles tiles strictly in tile order; more tiles in kSegs segments of
+// consecutive tiles, each summed in tile order, the segment sums then added in segment order.
+constexpr int kSeqTiles = 32, kSegs = 8;
+__host__ __device__ inline int seg_len(int ntiles) { return ntiles <= kSeqTiles ? ntiles : (ntiles + kSegs - 1) / kSegs; }
+
+// sum of the records [t_begin, t_end) of column c, tile order; partials: [tile][width][4] = sum, sumsq, min, max
+__device__ __forceinline__ void sum_records(const double *__restrict__ partials, int width, int c, int t_begin, int t_end,
+                                            double &s0, double &s1, double &lo, double &hi)
+{
+    s0 = 0.0; s1 = 0.0; lo = (double)FLT_MAX; hi = -(double)FLT_MAX;
+#pragma unroll 8
+    for (int t = t_begin; t < t_end; t++) { // loads are hoisted by the unrolling, the adds stay in order
+        const double *p = partials + ((long long)t * width + c) * 4;
+        s0 += __ldcg(p); s1 += __ldcg(p + 1);
+        lo = fmin(lo, __ldcg(p + 2)); hi = fmax(hi, __ldcg(p + 3));
+    }
+}
+
+// Group total of column c in the canonical order. Called by threads tid < kSegs * width of ONE CTA (thread = (segment,
+// column)); s_seg: kSegs * width * 4 doubles of shared memory. Contains __syncthreads: every thread of the CTA must call it.
+// The result is valid in threads tid < width.
+__device__ __forceinline__ void group_total(const double *__restrict__ partials, int width, int tile0, int ntiles, int tid,
+                                            int nthreads, double *s_seg, int c_of_tid, double &s0, double &s1, double &lo, double &hi)
+{
+    if (ntiles <= kSeqTiles) { // short groups: plain tile order, no exchange (c_of_tid: the column this thread finalises)
+        if (tid < width) sum_records(partials, width, c_of_tid, tile0, tile0 + ntiles, s0, s1, lo, hi);
+        return;
+    }
+    const int len = seg_len(ntiles);
+    for (int i = tid; i < kSegs * width; i += nthreads) {
+        const int seg = i / width, c = i - seg * width;
+        const int b = min(ntiles, seg * len), e = min(ntiles, b + len);
+        double a0, a1, l, h;
+        sum_records(partials, width, c, tile0 + b, tile0 + e, a0, a1, l, h);
+        double *o = s_seg + (size_t)i * 4;
+        o[0] = a0; o[1] = a1; o[2] = l; o[3] = h;
+    }
+    __syncthreads();
+    if (tid < width) {
+        s0 = 0.0; s1 = 0.0; lo = (double)FLT_MAX; hi = -(double)FLT_MAX;
+        for (int seg = 0; seg < kSegs; seg++) {
+            const double *o = s_seg + ((size_t)seg * width + c_of_tid) * 4;
+            s0 += o[0]; s1 += o[1];
+            lo = fmin(lo, o[2]); hi = fmax(hi, o[3]);
+        }
+    }
+}
+
 // In-place (x - mean) [* scale] over one tile's rows, 128-bit accesses on the 16-byte aligned body of the tile's contiguous
 // region; columns tracked incrementally (no division in the loop). Used by K3 (k_normalize_tiles) and by the normaliser
 // roles of the long-utterance scheme, so both give the same bits. s_ms: 2 * width floats of shared memory.
@@ -430,18 +506,24 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         __shared__ int s_role;
         if (tid == 0) {
             const int t = atomicAdd(a.work_counter, 1);
-            if (t == 2 * a.ntiles_launch - 1) *a.work_counter = 0; // every ticket of this launch is out: ready for the next
+            if (t == (int)gridDim.x - 1) *a.work_counter = 0; // every ticket of this launch is out: ready for the next
             s_role = t;
         }
         __syncthreads();
         tile_local = s_role;
         if (tile_local >= a.ntiles_launch) {
-            dev::normalise_role(a, a.tiles[a.tile_base + tile_local - a.ntiles_launch], reinterpret_cast<float *>(smem));
+            // normaliser role j of n_norm = gridDim.x - ntiles_launch: tiles j, j + n_norm, ...
+            const int n_norm = (int)gridDim.x - a.ntiles_launch;
+            for (int j = tile_local - a.ntiles_launch; j < a.ntiles_launch; j += n_norm) {
+                dev::normalise_role(a, dev::load_tile(a, a.tile_base + j), reinterpret_cast<float *>(smem));
+                __syncthreads();
+            }
             return;
         }
     }
     const int tile_idx = a.tile_base + tile_local;
-    const Tile tl = a.tiles[tile_idx];
+    const Tile tl = dev::load_tile(a, tile_idx);
+    const int q1 = (tl.flags & kTileQ1All) ? 2 : a.q1;
     const int D = a.l1 + a.l2, cols = a.cols;
     const int c0f = max(0, tl.t0 - D), c1f = min(tl.T, tl.t0 + tl.nout + D);
     const int ncomp = c1f - c0f;
@@ -637,8 +719,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
     const int n_stats = a.stats_rows_mode == 1 ? T - D : a.stats_rows_mode == 2 ? T : a.stats_rows_mode == 3 ? a.stats_count : 0;
     // source of this thread's column: src[r * cols]; statics of the Q1 rows come from D rows earlier
     const float *src = strm == 0 ? s_cep + (t0 - c0f) * cols + c : strm == 1 ? s_dhat + l2 * cols + c : s_dd + c;
-    const int rq = (a.q1 && strm == 0) ? (a.q1 == 2 ? 0 : max(0, T - D - t0)) : nout; // first row written with the shifted static
-    const int rs = a.stats_rows_mode == 3 ? nout : min(nout, max(0, n_stats - t0)); // rows [0, rs) enter the statistics
+    const int rq = (q1 && strm == 0) ? (q1 == 2 ? 0 : max(0, T - D - t0)) : nout; // first row written with the shifted static
+    const int rs = (tl.flags & kTileNoStats) ? 0 : a.stats_rows_mode == 3 ? nout : min(nout, max(0, n_stats - t0)); // rows [0, rs) enter the statistics
     const bool fast3 = a.nstreams == 3 && l1 == 3 && l2 == 3;
     if (fast3 && a.use_last) {
         // flush block of the streaming object: the previous block's statistics (mfcccpu.cpp:389), rows written normalised
@@ -798,14 +880,14 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         __syncthreads();
         if (s_last) {
             __threadfence();
-            if (tid < width) {
+            double s0, s1, lo, hi;
+            {
+                // records of the group's tiles in the canonical order (segments in parallel for long utterances)
+                double *s_seg = reinterpret_cast<double *>(smem + L.off_mags + 1024); // clear of s_mean / s_scale
                 const int src_col = a.norm_after_dyn ? tid : tid % cols;
-                double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
-                for (int t = 0; t < tl.ntiles; t++) {
-                    const double *p = a.partials + ((long long)(tl.tile0 + t) * width + src_col) * 4;
-                    s0 += __ldcg(p); s1 += __ldcg(p + 1);
-                    lo = fmin(lo, __ldcg(p + 2)); hi = fmax(hi, __ldcg(p + 3));
-                }
+                dev::group_total(a.partials, width, tl.tile0, tl.ntiles, tid, kFusedThreads, s_seg, tid < width ? src_col : 0, s0, s1, lo, hi);
+            }
+            if (tid < width) {
                 const double n = (double)n_stats;
                 float m = (float)(s0 / n), sc = 1.f;
                 if (a.norm_type == AFE_NORM_CVN) sc = (float)sqrt((n - 1.0) / (s1 - s0 * (s0 / n)));
@@ -827,7 +909,8 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             __syncthreads();
             if (active) { // same (row group, column) ownership as the row writer: no division in the loop
                 // rows of the group = first tile's t0 .. last tile's end (the whole utterance, or a block of a stream)
-                const int rb = a.tiles[tl.tile0].t0, re = a.tiles[tl.tile0 + tl.ntiles - 1].t0 + a.tiles[tl.tile0 + tl.ntiles - 1].nout;
+                const Tile tf = dev::load_tile(a, tl.tile0), tz = dev::load_tile(a, tl.tile0 + tl.ntiles - 1);
+                const int rb = tf.t0, re = tz.t0 + tz.nout;
                 float *o = a.out + (tl.out_row0 + rb) * (long long)width + col;
                 const float m = s_mean[col], sc = a.norm_type == AFE_NORM_CMN ? 1.f : s_scale[col];
                 const bool cmn = a.norm_type == AFE_NORM_CMN;

@@ -33,7 +33,13 @@ struct FusedEngine {
     void ensure_mel(float alpha);   // rebuilds the constant-bank tables when alpha changed (refresh_filters, mfcccpu.cpp:24-60)
     // Tiles for the output rows [t_first, t_first + n_out) of a sequence of T frames whose PCM starts at sample pcm_off;
     // output row of frame t = out_row0 + t. Appends to `tiles`; returns the number of tiles added.
-    int plan_rows(std::vector<Tile> &tiles, long long pcm_off, long long out_row0, int T, int t_first, int n_out, int group) const;
+    // nout_cap: largest tile (output frames), 0 = as large as the kernel's cepstra buffer allows (best throughput for big
+    // batches); the streaming object passes a smaller one so that a single block spreads over the whole GPU.
+    int plan_rows(std::vector<Tile> &tiles, long long pcm_off, long long out_row0, int T, int t_first, int n_out, int group,
+                  int nout_cap = 0) const;
+    // the split plan_rows makes: ntile tiles of nout output frames each (the last one shorter)
+    void plan_uniform(int T, int t_first, int n_out, int nout_cap, int &ntile, int &nout) const;
+    int latency_tile(int n_out) const; // nout_cap that cuts n_out rows into about two tiles per SM (whole 32-frame rounds)
     // Arguments common to every launch; the caller fills pcm/out/tiles and the statistics / normalisation fields.
     FusedArgs base_args(int flags_q1, bool use_tma) const;
     bool cluster_schedulable(int cluster, const FusedArgs &a, cudaStream_t st);

@@ -1,4 +1,6 @@
 // One instantiation of the fused kernel per translation unit: nvcc -DAFE_INST_KEY=<0..23> (see the Makefile).
+#include <atomic>
+
 #include "afe_internal.h"
 #include "afe_fused_launch.h"
 
@@ -28,10 +30,24 @@ void fill(cudaLaunchConfig_t &cfg, cudaLaunchAttribute &attr, const FusedLaunch 
 #define AFE_CAT2(a, b) a##b
 #define AFE_CAT(a, b) AFE_CAT2(a, b)
 
+// cudaFuncSetAttribute is a slow, serialising call: once per device and shared-memory size, not per launch
+static cudaError_t ensure_smem_attr(int bytes)
+{
+    static std::atomic<int> done[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (done[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_fused_mfcc<kN2, kNZ, 8, kKF, kPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[dev].store(bytes, std::memory_order_release);
+    return e;
+}
+
 cudaError_t AFE_CAT(fused_launch_, AFE_INST_KEY)(const FusedLaunch &fl)
 {
     auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF, kPre>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.L.total);
+    cudaError_t e = ensure_smem_attr(fl.L.total);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
     fill(cfg, attr, fl);
@@ -41,7 +57,7 @@ cudaError_t AFE_CAT(fused_launch_, AFE_INST_KEY)(const FusedLaunch &fl)
 int AFE_CAT(fused_max_clusters_, AFE_INST_KEY)(const FusedLaunch &fl)
 {
     auto kern = k_fused_mfcc<kN2, kNZ, 8, kKF, kPre>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fl.L.total) != cudaSuccess) return -1;
+    if (ensure_smem_attr(fl.L.total) != cudaSuccess) return -1;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr;
     fill(cfg, attr, fl);
     int n = 0;

@@ -28,9 +28,11 @@ struct SegState {
     // pinned staging (two buffers, alternating) so that the H2D copy is asynchronous and the caller may reuse its buffer
     // at once; a buffer is reused only after the copy that read it has completed (event), which by then it normally has
     int16_t *h_pin[2] = {nullptr, nullptr};
-    cudaEvent_t ev_pin[2] = {nullptr, nullptr};
+    bool pin_busy[2] = {false, false}; // an H2D copy out of this staging buffer may still be running; cleared by synced()
     size_t pin_cap = 0;
     int cur = 0, pin = 0;
+    bool carry_pending = false; // the tail of buf[cur] still has to move to the front of buf[cur ^ 1] (done by the next set_input;
+                                // flush() reads the tail where it lies, so a single-block stream never copies it)
     float pre = 0.f;          // pre-emphasis coefficient (staged segmenter path)
 
     void init(int W_, int S_, int frame_cap_, int D_)
@@ -45,7 +47,6 @@ struct SegState {
         pin_cap = cap;
         for (int i = 0; i < 2; i++) {
             AFE_CUDA(cudaMallocHost(&h_pin[i], sizeof(int16_t) * std::max<size_t>(pin_cap, 1)));
-            AFE_CUDA(cudaEventCreateWithFlags(&ev_pin[i], cudaEventDisableTiming));
         }
     }
     void release()
@@ -53,17 +54,23 @@ struct SegState {
         buf[0].release(); buf[1].release();
         for (int i = 0; i < 2; i++) {
             if (h_pin[i]) cudaFreeHost(h_pin[i]);
-            if (ev_pin[i]) cudaEventDestroy(ev_pin[i]);
-            h_pin[i] = nullptr; ev_pin[i] = nullptr;
+            h_pin[i] = nullptr;
         }
     }
-    void reset() { remaining = samples = 0; flushed = true; last_calc_flushed = false; }
+    void reset() { remaining = samples = 0; flushed = true; last_calc_flushed = false; carry_pending = false; }
+    void synced() { pin_busy[0] = pin_busy[1] = false; } // the owner synchronised the stream: every staged copy has landed
     int est(int n) const { return afe_estimated_window_count(n, W, S); }
 
     // Returns the device pointer holding this block's contiguous PCM (valid until the next call).
     const int16_t *set_input(const int16_t *in, int n, int &wc, int &wc_nd, cudaStream_t st)
     {
         if ((size_t)n + (flushed ? 0 : remaining) > cap) throw Error("Can't process data, buffer is too small");
+        if (!flushed && carry_pending) {                     // carry-over to the front of the other buffer, then append
+            const int16_t *src = buf[cur].p + samples - remaining;
+            AFE_CUDA(cudaMemcpyAsync(buf[cur ^ 1].p, src, sizeof(int16_t) * remaining, cudaMemcpyDeviceToDevice, st));
+            cur ^= 1;
+        }
+        carry_pending = false;
         int16_t *dst = buf[cur].p;
         int total = n;
         if (flushed) {                                       // first block of a stream (segmentercpu.cpp:59-75)
@@ -78,17 +85,16 @@ struct SegState {
         }
         last_calc_flushed = flushed;
         pin ^= 1;
-        AFE_CUDA(cudaEventSynchronize(ev_pin[pin]));         // the copy that last read this staging buffer is done
+        if (pin_busy[pin]) { AFE_CUDA(cudaStreamSynchronize(st)); synced(); } // rare: two blocks without a get_output between
         memcpy(h_pin[pin], in, sizeof(int16_t) * n);
+        pin_busy[pin] = true;
         if (flushed) {
             AFE_CUDA(cudaMemcpyAsync(dst, h_pin[pin], sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
-            AFE_CUDA(cudaEventRecord(ev_pin[pin], st));
             const int used = (wc - D) * S + W - S;
             remaining = total - used + W - S;
             flushed = false;
         } else {                                             // append to the carry-over (segmentercpu.cpp:76-93)
             AFE_CUDA(cudaMemcpyAsync(dst + remaining, h_pin[pin], sizeof(int16_t) * n, cudaMemcpyHostToDevice, st));
-            AFE_CUDA(cudaEventRecord(ev_pin[pin], st));
             total = n + remaining;
             wc_nd = est(total);
             wc = wc_nd - 2 * D;
@@ -99,19 +105,16 @@ struct SegState {
         samples = total;
         return dst;
     }
-    // after the frames of the current block were consumed: move the tail to the front of the other buffer
-    void carry(cudaStream_t st)
-    {
-        const int16_t *src = buf[cur].p + samples - remaining;
-        AFE_CUDA(cudaMemcpyAsync(buf[cur ^ 1].p, src, sizeof(int16_t) * remaining, cudaMemcpyDeviceToDevice, st));
-        cur ^= 1;
-    }
+    // after the frames of the current block were cut: its tail is the next block's head (moved lazily, see carry_pending)
+    void carry(cudaStream_t) { carry_pending = true; }
     const int16_t *flush(int &wc, int &wc_nd)                // segmentercpu.cpp:97-106
     {
         flushed = true;
         wc_nd = est(remaining);
         wc = wc_nd - D;
-        return buf[cur].p;
+        const int16_t *src = carry_pending ? buf[cur].p + samples - remaining : buf[cur].p;
+        carry_pending = false;
+        return src;
     }
 };
 
@@ -131,9 +134,15 @@ struct afe_mfcc {
     // ---- fused route: every block is ONE launch of K1
     std::unique_ptr<FusedEngine> eng;
     const int16_t *blk_pcm = nullptr;   // device PCM of the current block (carry-over + new samples)
-    DevBuf<Tile> d_tiles;
-    Tile *h_tiles = nullptr; size_t tiles_cap = 0;
-    cudaEvent_t ev_tiles = nullptr;     // the tile upload of the previous apply() has been consumed
+    size_t tiles_cap = 0;
+    // Speculative flush rows: every apply() of a non-final block also computes, in the same launch, the D rows a flush()
+    // right after it would return (outb rows [wc, wc + D)). flush() -> apply() -> get_output_data() then costs no launch
+    // as long as alpha and the Q1 option are still the ones those rows were computed with.
+    bool spec_valid = false, spec_fix_q1 = false, out_is_spec = false;
+    float spec_alpha = 0.f;
+    int spec_row0 = 0;
+    bool spec_on_host = false;          // the speculative rows already travelled to h_out with the block's rows
+    bool pending = false;               // work enqueued on the stream since the last synchronisation
     DevBuf<double> partials;
     DevBuf<int> counters;               // [1] arrival tickets + [1] role tickets
     DevBuf<unsigned> flags;
@@ -189,12 +198,9 @@ int afe_mfcc_create(const afe_params *p, int cuda_device, afe_mfcc **out)
         const bool fused = fused_unsupported_reason(d).empty() && (d.p.norm == AFE_NORM_NONE || d.p.norm_after_dyn);
         if (fused) {
             h->eng.reset(new FusedEngine(d, cuda_device));
-            h->tiles_cap = fc / std::max(1, h->eng->nout_max / 2) + 8;
-            h->d_tiles.alloc(h->tiles_cap);
-            AFE_CUDA(cudaMallocHost(&h->h_tiles, sizeof(Tile) * h->tiles_cap));
-            AFE_CUDA(cudaEventCreateWithFlags(&h->ev_tiles, cudaEventDisableTiming));
+            h->tiles_cap = fc / 32 + 2 * (size_t)h->eng->sm_count + 8;
             if (d.p.norm != AFE_NORM_NONE) {
-                h->partials.alloc(h->tiles_cap * 4 * d.width);
+                h->partials.alloc((h->tiles_cap + 1) * 4 * d.width);
                 h->counters.alloc(2); h->flags.alloc(1);
                 AFE_CUDA(cudaMemset(h->counters.p, 0, sizeof(int) * 2));
                 AFE_CUDA(cudaMemset(h->flags.p, 0, sizeof(unsigned)));
@@ -202,8 +208,8 @@ int afe_mfcc_create(const afe_params *p, int cuda_device, afe_mfcc **out)
             }
         } else
             alloc_staged(h.get());
-        h->outb.alloc(fc * d.width);
-        h->h_out_cap = fc * d.width;
+        h->outb.alloc((fc + d.D) * d.width);
+        h->h_out_cap = (fc + d.D) * d.width;
         AFE_CUDA(cudaMallocHost(&h->h_out, sizeof(float) * h->h_out_cap));
         *out = h.release();
     });
@@ -217,8 +223,6 @@ void afe_mfcc_destroy(afe_mfcc *h)
     h->eng.reset();
     h->fft.release(); h->mel.release(); h->seg.release();
     if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->h_tiles) cudaFreeHost(h->h_tiles);
-    if (h->ev_tiles) cudaEventDestroy(h->ev_tiles);
     cudaStreamDestroy(h->st);
     delete h;
 }
@@ -261,7 +265,11 @@ int afe_mfcc_set_option(afe_mfcc *h, int option, int value)
 }
 int afe_mfcc_reset(afe_mfcc *h)
 {
-    return guarded([&] { DeviceGuard g(h->device); AFE_CUDA(cudaStreamSynchronize(h->st)); h->seg.reset(); h->last_block = false; });
+    return guarded([&] {
+        DeviceGuard g(h->device);
+        if (h->pending) { AFE_CUDA(cudaStreamSynchronize(h->st)); h->pending = false; h->seg.synced(); }
+        h->seg.reset(); h->last_block = false; h->spec_valid = false; h->out_is_spec = false; h->spec_on_host = false;
+    });
 }
 
 int afe_mfcc_set_input(afe_mfcc *h, const int16_t *data, int samples, int *frames)
@@ -272,6 +280,8 @@ int afe_mfcc_set_input(afe_mfcc *h, const int16_t *data, int samples, int *frame
         if (samples > h->d.in_cap) throw Error("Can't process data, buffer is too small");   // mfcccpu.cpp:338-339
         DeviceGuard g(h->device);
         int wc, wc_nd;
+        h->spec_valid = false; h->out_is_spec = false; h->spec_on_host = false;
+        h->pending = true;
         const int16_t *pcm = h->seg.set_input(data, samples, wc, wc_nd, h->st);
         h->blk_pcm = pcm; // stays intact in its ping-pong buffer until the set_input after the next one
         if (!h->fused() && wc > 0) launch_fft_mag(h->d, h->fft, h->mel, pcm, h->mag.p, wc_nd, h->st, h->pre); // segment + fft fused
@@ -328,26 +338,29 @@ static void normalise(afe_mfcc *h, int wc, bool use_last)
 //   first block   t_first = 0, left edge replicated by index clamping, D look-ahead frames on the right
 //   middle block  t_first = D, context on both sides comes from the carried-over samples
 //   flush block   t_first = D, right edge replicated; normalised with the previous block's statistics
-// (mfcccpu.cpp:371-425; do_delta :234-263). Rows land in outb[0 .. wc).
+// (mfcccpu.cpp:371-425; do_delta :234-263). Rows land in outb[0 .. wc). The tiles are described in the kernel arguments
+// (FusedArgs::blk_*), so an apply() is ONE driver call: the launch.
 static void apply_fused(afe_mfcc *h, int wc, int wc_nd, bool first, bool last)
 {
     const Derived &d = h->d;
     FusedEngine &eng = *h->eng;
     eng.ensure_mel(h->alpha);
     const int t_first = first ? 0 : d.D;
-    std::vector<Tile> tiles;
-    const int ntiles = eng.plan_rows(tiles, 0, -(long long)t_first, wc_nd, t_first, wc, 0);
-    if ((size_t)ntiles > h->tiles_cap) throw Error("block needs more tiles than the object was sized for");
-    AFE_CUDA(cudaEventSynchronize(h->ev_tiles));             // the previous upload has left the pinned table
-    memcpy(h->h_tiles, tiles.data(), sizeof(Tile) * ntiles);
-    AFE_CUDA(cudaMemcpyAsync(h->d_tiles.p, h->h_tiles, sizeof(Tile) * ntiles, cudaMemcpyHostToDevice, h->st));
-    AFE_CUDA(cudaEventRecord(h->ev_tiles, h->st));
+    // small tiles: ONE block should occupy the whole GPU (a 512-frame tile is ~90 us of serial work for one CTA)
+    int ntiles, nout;
+    eng.plan_uniform(wc_nd, t_first, wc, eng.latency_tile(wc), ntiles, nout);
+    if ((size_t)ntiles + 1 > h->tiles_cap) throw Error("block needs more tiles than the object was sized for");
     const bool tma = d.S % 8 == 0 && (reinterpret_cast<uintptr_t>(h->blk_pcm) & 15) == 0;
     // quirk Q1: flushing after a single set_input reads every static D rows early (static_row_offset() == 0 there)
-    const int q1 = (last && h->static_row_offset() == 0) ? 2 : 0;
-    FusedArgs a = eng.base_args(q1, tma);
-    a.pcm = h->blk_pcm; a.out = h->outb.p; a.tiles = h->d_tiles.p; a.tile_base = 0;
-    int grid = ntiles, cluster = 0;
+    const bool q1_flush = h->seg.last_calc_flushed && !h->fix_q1;
+    FusedArgs a = eng.base_args((last && q1_flush) ? 2 : 0, tma);
+    a.pcm = h->blk_pcm; a.out = h->outb.p; a.tiles = nullptr; a.tile_base = 0;
+    a.blk_ntiles = ntiles; a.blk_T = wc_nd; a.blk_t_first = t_first; a.blk_n_out = wc; a.blk_nout = nout;
+    // the rows a flush() right after this block would return ride along as one more tile (rows [wc, wc + D) of outb)
+    const bool spec = !last && d.D > 0 && wc_nd >= 2 * d.D;
+    a.blk_spec = spec ? 1 : 0; a.blk_spec_q1 = q1_flush ? 1 : 0;
+    const int total = ntiles + (spec ? 1 : 0);
+    int grid = total, cluster = 0;
     if (d.p.norm != AFE_NORM_NONE) {
         a.g_mean = h->g_mean.p; a.g_scale = h->g_scale.p;
         if (last) a.use_last = 1;                             // mfcccpu.cpp:389: use_last_stats
@@ -356,17 +369,21 @@ static void apply_fused(afe_mfcc *h, int wc, int wc_nd, bool first, bool last)
             a.stats_kind = d.p.norm == AFE_NORM_CMN ? 1 : d.p.norm == AFE_NORM_CVN ? 2 : 3;
             a.partials = h->partials.p;
             const bool fast3 = d.width == 3 * d.cols && d.l1 == 3 && d.l2 == 3;
-            if (fast3 && ntiles <= 4 && eng.cluster_schedulable(ntiles, a, h->st)) { a.cluster_norm = 1; cluster = ntiles; }
-            else if (ntiles <= 8) a.counters = h->counters.p;
-            else {
+            if (!spec && fast3 && total <= 4 && eng.cluster_schedulable(total, a, h->st)) { a.cluster_norm = 1; cluster = total; }
+            else if (!spec && total <= 8) a.counters = h->counters.p;
+            else { // role scheme: one launch, the statistics of the block are final before any row is normalised
                 a.counters = h->counters.p; a.work_counter = h->counters.p + 1;
-                a.flags = h->flags.p; a.epoch = ++h->epoch; a.ntiles_launch = ntiles;
-                grid = 2 * ntiles;
+                a.flags = h->flags.p; a.epoch = ++h->epoch; a.ntiles_launch = total;
+                grid = total + std::min(total, 2 * eng.sm_count);
             }
         }
     }
     eng.launch(a, grid, cluster, h->st);
     h->launches++;
+    h->pending = true;
+    h->out_is_spec = false; h->spec_on_host = false;
+    h->spec_valid = spec;
+    if (spec) { h->spec_alpha = h->alpha; h->spec_fix_q1 = h->fix_q1; h->spec_row0 = wc; }
 }
 
 int afe_mfcc_apply(afe_mfcc *h)
@@ -379,6 +396,11 @@ int afe_mfcc_apply(afe_mfcc *h)
         if (h->last_block) {                                   // mfcccpu.cpp:373-390
             wc_nd = h->seg.est(h->seg.remaining); wc = wc_nd - d.D; last = true; use_last = true;
             if (wc <= 0) return;
+            if (h->fused() && h->spec_valid && wc == d.D && h->spec_alpha == h->alpha && h->spec_fix_q1 == h->fix_q1) {
+                h->out_is_spec = true;                         // these rows were computed with the previous block
+                return;
+            }
+            h->spec_valid = false; h->out_is_spec = false;
         } else if (h->seg.last_calc_flushed) {                 // :391-407
             wc_nd = h->seg.est(h->seg.samples); wc = wc_nd - d.D; first = true;
             if (wc <= 0) throw Error("Can't process data, window count is too small");
@@ -408,8 +430,23 @@ int afe_mfcc_get_output(afe_mfcc *h, float *out, int frames)
         if (frames <= 0) return;
         DeviceGuard g(h->device);
         const size_t n = (size_t)frames * d.width;
-        AFE_CUDA(cudaMemcpyAsync(h->h_out, h->outb.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->st));
+        if (h->out_is_spec) {                                  // flush rows computed (and usually already fetched) with the block
+            if (frames > d.D) throw Error("Window count too high");
+            const size_t off = (size_t)h->spec_row0 * d.width;
+            if (!h->spec_on_host) {
+                AFE_CUDA(cudaMemcpyAsync(h->h_out + off, h->outb.p + off, sizeof(float) * d.D * d.width, cudaMemcpyDeviceToHost, h->st));
+                AFE_CUDA(cudaStreamSynchronize(h->st));
+                h->pending = false; h->seg.synced(); h->spec_on_host = true;
+            }
+            memcpy(out, h->h_out + off, sizeof(float) * n);
+            return;
+        }
+        // the speculative flush rows sit right behind the block's rows: one copy fetches both
+        const bool with_spec = h->spec_valid && frames == h->spec_row0;
+        const size_t n_copy = n + (with_spec ? (size_t)d.D * d.width : 0);
+        AFE_CUDA(cudaMemcpyAsync(h->h_out, h->outb.p, sizeof(float) * n_copy, cudaMemcpyDeviceToHost, h->st));
         AFE_CUDA(cudaStreamSynchronize(h->st));
+        h->pending = false; h->seg.synced(); h->spec_on_host = with_spec;
         memcpy(out, h->h_out, sizeof(float) * n);
     });
 }
@@ -472,6 +509,7 @@ int afe_segmenter_set_input(afe_segmenter *s, const int16_t *in, float *d_out, i
         if (*wc > 0) launch_segment(pcm, s->window.p, d_out, *wc_nd, s->seg.W, s->seg.S, s->seg.N2, s->st, s->seg.pre);
         s->seg.carry(s->st);
         AFE_CUDA(cudaStreamSynchronize(s->st));
+        s->seg.synced();
     });
 }
 int afe_segmenter_flush(afe_segmenter *s, float *d_out, int *wc, int *wc_nd)

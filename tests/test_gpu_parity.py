@@ -341,7 +341,11 @@ def test_stream_object_runs_the_fused_kernel():
     wc = m.set_input(pcm); m.apply(); m.get_output_data(wc)
     assert m.kernel_launches == 1
     wc = m.flush(); m.apply(); m.get_output_data(wc)
-    assert m.kernel_launches == 2
+    assert m.kernel_launches == 1            # the flush rows were computed speculatively by the block's launch
+    m.reset()
+    wc = m.set_input(pcm); m.set_alpha(0.9); m.apply(); m.get_output_data(wc)
+    wc = m.flush(); m.set_alpha(1.0); m.apply(); m.get_output_data(wc)
+    assert m.kernel_launches == 3            # alpha changed before the flush: the speculation is discarded, one more launch
     m.close()
     for kw in (dict(window_size=640), dict(shift=161), dict(norm=1, dyn=2, norm_after_dyn=0)):
         m = afe.MfccCuda(afe.make_params(input_buffer_size=BIG, **kw))
