@@ -88,7 +88,7 @@ void upload_window(const Derived &d, const float *window, MelTables &t, cudaStre
 
 // ------------------------------------------------------------------------------------------------ K2 / K3
 // stats record per group: [sum[w], sumsq[w], count, min[w], max[w]]  (4w+1 doubles)
-__global__ void k_reduce_partials(const double *__restrict__ partials, const int *__restrict__ tile_begin,
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, const int *__restrict__ tile_begin,
                                   const double *__restrict__ counts, int width, double *__restrict__ stats)
 {
     // the canonical summation order of dev::group_total, so that K2 and the in-kernel schemes agree bit for bit
@@ -105,17 +105,13 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, const int
 
 // Corpus scope has ONE group over all tiles: two deterministic levels instead of one serial loop.
 // level 1: block j sums tiles j, j+gridDim.x, ... -> scratch[j][width][4]; level 2 = k_reduce_partials over the scratch.
-__global__ void k_reduce_partials_level1(const double *__restrict__ partials, int n_tiles, int width,
+__global__ void __launch_bounds__(128) k_reduce_partials_level1(const double *__restrict__ partials, int n_tiles, int width,
                                          double *__restrict__ scratch)
 {
     const int c = threadIdx.x;
     if (c >= width) return;
-    double s0 = 0.0, s1 = 0.0, lo = (double)FLT_MAX, hi = -(double)FLT_MAX;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const double *p = partials + ((long long)t * width + c) * 4;
-        s0 += p[0]; s1 += p[1];
-        lo = fmin(lo, p[2]); hi = fmax(hi, p[3]);
-    }
+    double s0, s1, lo, hi;
+    dev::sum_records(partials, width, c, blockIdx.x, n_tiles, s0, s1, lo, hi, gridDim.x);
     double *o = scratch + ((long long)blockIdx.x * width + c) * 4;
     o[0] = s0; o[1] = s1; o[2] = lo; o[3] = hi;
 }
@@ -620,6 +616,30 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         const bool corpus = b->scope == AFE_STATS_CORPUS;
         bool aligned = d.S % 8 == 0;
         double corpus_count = 0;
+        // Wave balancing for small batches (a single long stream, a handful of files): with fewer than ~8 waves of CTAs the
+        // tail of a partly filled last wave costs a whole tile time, so pick the tile size for which
+        // waves x rounds-per-tile is smallest (config 5: 720 tiles x 16 rounds -> 4 full waves x 10 rounds).
+        int nout_cap = 0;
+        {
+            int64_t total = 0, longest = 0;
+            for (int u = 0; u < n_utts; u++) {
+                const int64_t T = std::max<int64_t>(0, (len[u] - (d.W - d.S)) / d.S);
+                total += T; longest = std::max(longest, T);
+            }
+            const int slots = 2 * eng.sm_count;
+            const int64_t tiles_default = (total + eng.nout_max - 1) / eng.nout_max;
+            // only batches that hold a long utterance (more than 8 tiles: the role scheme anyway); batches of short
+            // utterances keep the large tiles, whose 1..4-tile utterances normalise inside a thread-block cluster
+            if (longest > 8 * (int64_t)eng.nout_max && tiles_default <= 8 * (int64_t)slots) {
+                const int w0 = (int)((tiles_default + slots - 1) / slots);
+                int best_cost = w0 * ((eng.nout_max + 2 * d.D + kRoundFrames - 1) / kRoundFrames);
+                for (int w = w0; w <= w0 + 3; w++) {
+                    const int cap = (int)std::min<int64_t>(eng.nout_max, std::max<int64_t>(1, (total + (int64_t)w * slots - 1) / ((int64_t)w * slots)));
+                    const int rounds = std::max(2, (cap + 2 * d.D + kRoundFrames - 1) / kRoundFrames);
+                    if (w * rounds < best_cost) { best_cost = w * rounds; nout_cap = std::max(1, std::min(eng.nout_max, rounds * kRoundFrames - 2 * d.D)); }
+                }
+            }
+        }
         for (int u = 0; u < n_utts; u++) {
             const int64_t n = len[u];
             if (n < 0 || n > 0x7fffffff || off[u] < 0) throw Error("plan: invalid utterance offset/length");
@@ -633,7 +653,7 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             b->frame_off[u + 1] = b->frame_off[u] + T;
             b->h_tile_begin[u] = (int)tiles.size();
             if (!corpus) tile_begin.push_back((int)tiles.size());
-            const int ntile = eng.plan_rows(tiles, off[u], b->frame_off[u], T, 0, T, corpus ? 0 : u);
+            const int ntile = eng.plan_rows(tiles, off[u], b->frame_off[u], T, 0, T, corpus ? 0 : u, nout_cap);
             b->max_tiles_per_utt = std::max(b->max_tiles_per_utt, ntile);
             const double cnt = !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
             if (corpus) corpus_count += cnt; else counts.push_back(cnt);

@@ -371,19 +371,53 @@ __device__ __forceinline__ Tile load_tile(const FusedArgs &a, int idx)
 // Canonical order in which the per-tile statistics records of one group are summed (every scheme - cluster, ticket, role
 // scheme, K2 - must produce the same bits): up to kSeqTiles tiles strictly in tile order; more tiles in kSegs segments of
 // consecutive tiles, each summed in tile order, the segment sums then added in segment order.
-constexpr int kSeqTiles = 32, kSegs = 8;
+constexpr int kSeqTiles = 32, kSegs = 6;
 __host__ __device__ inline int seg_len(int ntiles) { return ntiles <= kSeqTiles ? ntiles : (ntiles + kSegs - 1) / kSegs; }
 
-// sum of the records [t_begin, t_end) of column c, tile order; partials: [tile][width][4] = sum, sumsq, min, max
+static __device__ unsigned g_opaque_zero = 0; // never written
+
+// sum of the records [t_begin, t_end) of column c, tile order; partials: [tile][width][4] = sum, sumsq, min, max.
+// Eight records (sixteen 16-byte loads) are in flight before the first add: the records come from L2, and a loop that
+// loads and adds one record at a time costs a full L2 round trip per tile (163 us for 1169 tiles, profiles/r02_c5_launches.csv).
+// PLAIN (weak) loads on purpose: ptxas keeps `ld.global.cg` / __ldcg loads next to their consumers (measured: two loads in
+// flight), while it batches ordinary loads. They are correct here: every caller reads the records after the synchronising
+// pattern "ticket atomic -> __syncthreads -> __threadfence" (or in a later kernel), which orders them after the writers'
+// "stores -> __threadfence -> ticket atomic" and drops stale L1 lines.
 __device__ __forceinline__ void sum_records(const double *__restrict__ partials, int width, int c, int t_begin, int t_end,
-                                            double &s0, double &s1, double &lo, double &hi)
+                                            double &s0, double &s1, double &lo, double &hi, int tstep = 1)
 {
     s0 = 0.0; s1 = 0.0; lo = (double)FLT_MAX; hi = -(double)FLT_MAX;
-#pragma unroll 8
-    for (int t = t_begin; t < t_end; t++) { // loads are hoisted by the unrolling, the adds stay in order
-        const double *p = partials + ((long long)t * width + c) * 4;
-        s0 += __ldcg(p); s1 += __ldcg(p + 1);
-        lo = fmin(lo, __ldcg(p + 2)); hi = fmax(hi, __ldcg(p + 3));
+    constexpr int U = 8;
+    const size_t stride = (size_t)width * 4 * tstep;   // records t_begin, t_begin + tstep, ... below t_end
+    const double *p = partials + ((size_t)t_begin * width + c) * 4;
+    const int last = t_end - 1;
+    const unsigned z = *reinterpret_cast<volatile unsigned *>(&g_opaque_zero); // a zero neither NVVM nor ptxas can see through
+    for (int t = t_begin; t < t_end; t += U * tstep, p += U * stride) {
+        double2 a[U], b[U];
+        // unconditional loads (a record past the end re-reads the last valid one and is discarded below): predicated loads
+        // share the predicate registers with the min / max compares and ptxas then serialises them (two L2 round trips per
+        // four records in the first version of this loop)
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const double2 *q = reinterpret_cast<const double2 *>(t + k * tstep <= last ? p + k * stride : p);
+            a[k] = q[0];
+            b[k] = q[1];
+        }
+        // All sixteen loads must be ISSUED before the first add. ptxas schedules each load right in front of its consumer
+        // (load, add, load, add: an L2 round trip per record) and looks through empty asm barriers, so the first summand is
+        // made to depend on every loaded word through an OR with `z`, a zero the compiler cannot see (bits unchanged).
+        unsigned all = 0;
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            all |= (unsigned)__double2hiint(a[k].x) | (unsigned)__double2hiint(a[k].y) | (unsigned)__double2hiint(b[k].x) |
+                   (unsigned)__double2hiint(b[k].y);
+        a[0].x = __hiloint2double(__double2hiint(a[0].x) | (int)(all & z), __double2loint(a[0].x));
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const bool ok = t + k * tstep <= last; // tile order; adding 0.0 / comparing with the identity changes no bits
+            s0 += ok ? a[k].x : 0.0; s1 += ok ? a[k].y : 0.0;
+            lo = fmin(lo, ok ? b[k].x : (double)FLT_MAX); hi = fmax(hi, ok ? b[k].y : -(double)FLT_MAX);
+        }
     }
 }
 
@@ -447,15 +481,26 @@ __device__ __forceinline__ void normalise_tile_rows(float *__restrict__ out, con
     float4 *p4 = reinterpret_cast<float4 *>(base + head);
     int c = (head + 4 * (int)threadIdx.x) % width;
     const int cstep = (4 * (int)blockDim.x) % width;
-    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
-        float4 v = __ldcg(p4 + j);
-        int c1 = c + 1; if (c1 >= width) c1 -= width;
-        int c2 = c1 + 1; if (c2 >= width) c2 -= width;
-        int c3 = c2 + 1; if (c3 >= width) c3 -= width;
-        v.x -= m[c]; v.y -= m[c1]; v.z -= m[c2]; v.w -= m[c3];
-        if (!cmn) { v.x *= sc[c]; v.y *= sc[c1]; v.z *= sc[c2]; v.w *= sc[c3]; }
-        p4[j] = v;
-        c += cstep; if (c >= width) c -= width;
+    constexpr int U = 4; // loads in flight per thread: the rows come from L2 (~300 cycles away)
+    const int bd = blockDim.x;
+    for (int j = threadIdx.x; j < n4; j += U * bd) {
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (j + k * bd < n4) v[k] = __ldcg(p4 + j + k * bd);
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            if (j + k * bd < n4) {
+                int c1 = c + 1; if (c1 >= width) c1 -= width;
+                int c2 = c1 + 1; if (c2 >= width) c2 -= width;
+                int c3 = c2 + 1; if (c3 >= width) c3 -= width;
+                float4 w = v[k];
+                w.x -= m[c]; w.y -= m[c1]; w.z -= m[c2]; w.w -= m[c3];
+                if (!cmn) { w.x *= sc[c]; w.y *= sc[c1]; w.z *= sc[c2]; w.w *= sc[c3]; }
+                p4[j + k * bd] = w;
+            }
+            c += cstep; if (c >= width) c -= width;
+        }
     }
 }
 

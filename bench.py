@@ -566,10 +566,10 @@ def leg_config5(cx, args, steps):
     offs, lens = np.zeros(1, np.int64), np.full(1, n, np.int64)
     peak = float(cx.peaks.get("hbm_gbs", 6650.0))
     res = {}
-    for name, norm in (("no_norm", 0), ("cmn", 1)):
+    for name, norm, fl in (("no_norm", 0, 0), ("cmn", 1, 0), ("cmn_k2_k3_kernels", 1, afe.BATCH_UNFUSED_NORM)):
         p = params_dict(g, norm)
         ap = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in p.items() if k != "alpha"})
-        b = afe.BatchMfcc(ap, cx.local, flags=afe.BATCH_Q1_EXACT)
+        b = afe.BatchMfcc(ap, cx.local, flags=afe.BATCH_Q1_EXACT | fl)
         b.set_stream(stream.cuda_stream)
         assert b.plan(offs, lens) == T
         for _ in range(3):
