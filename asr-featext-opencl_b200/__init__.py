@@ -38,10 +38,10 @@ afe_normalizer_set_stats
 afe_device_malloc afe_device_free afe_memcpy_h2d afe_memcpy_d2h
 afe_batch_create afe_batch_destroy afe_batch_set_window afe_batch_set_alpha afe_batch_set_preemphasis afe_batch_set_options
 afe_batch_set_stream
-afe_batch_plan afe_batch_frame_offsets afe_batch_num_tiles afe_batch_kernel_launches afe_batch_kernel_name afe_batch_run_device
+afe_batch_plan afe_batch_plan_segments afe_batch_frame_offsets afe_batch_num_tiles afe_batch_kernel_launches afe_batch_kernel_name afe_batch_run_device
 afe_batch_extract_device afe_batch_corpus_stats afe_batch_normalizer afe_batch_set_corpus_stats
 afe_batch_normalize_device afe_batch_synchronize afe_batch_run_host
-afe_cmvn_finalize_host afe_shard_utterances afe_nccl_get_unique_id afe_nccl_comm_init afe_nccl_comm_destroy
+afe_cmvn_finalize_host afe_shard_utterances afe_shard_stream afe_nccl_get_unique_id afe_nccl_comm_init afe_nccl_comm_destroy
 """.split()
 
 
@@ -141,6 +141,8 @@ def lib():
             "afe_batch_set_options": (C.c_int, [vp, C.c_int, C.c_int]),
             "afe_batch_set_stream": (C.c_int, [vp, vp]),
             "afe_batch_plan": (C.c_int, [vp, i64p, i64p, C.c_int, i64p]),
+            "afe_batch_plan_segments": (C.c_int, [vp, i64p, i64p, ip, ip, C.c_int, i64p]),
+            "afe_shard_stream": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, i64p, ip, ip]),
             "afe_batch_frame_offsets": (C.c_int, [vp, i64p]),
             "afe_batch_num_tiles": (C.c_int, [vp]),
             "afe_batch_kernel_launches": (C.c_int, [vp]),
@@ -211,6 +213,17 @@ def shard_utterances(sample_lengths, n_ranks):
     _check(lib().afe_shard_utterances(off.ctypes.data_as(C.POINTER(C.c_longlong)), len(off), n_ranks,
                                       starts.ctypes.data_as(C.POINTER(C.c_int))))
     return starts
+
+
+def shard_stream(total_samples, window_size, shift, delta_frames, n_ranks):
+    """-> dict of arrays: sample_begin, sample_count, first, count, local_first (afe_shard_stream)."""
+    sb, sc, fi = (np.zeros(n_ranks, np.int64) for _ in range(3))
+    cnt, lf = np.zeros(n_ranks, np.int32), np.zeros(n_ranks, np.int32)
+    i64p, ip = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+    _check(lib().afe_shard_stream(int(total_samples), int(window_size), int(shift), int(delta_frames), int(n_ranks),
+                                  sb.ctypes.data_as(i64p), sc.ctypes.data_as(i64p), fi.ctypes.data_as(i64p),
+                                  cnt.ctypes.data_as(ip), lf.ctypes.data_as(ip)))
+    return dict(sample_begin=sb, sample_count=sc, first=fi, count=cnt, local_first=lf)
 
 
 def cmvn_finalize_host(norm, width, stats):
@@ -531,6 +544,22 @@ class BatchMfcc:
         total = C.c_longlong(0)
         i64p = C.POINTER(C.c_longlong)
         _check(lib().afe_batch_plan(self._h, off.ctypes.data_as(i64p), ln.ctypes.data_as(i64p), len(off), C.byref(total)))
+        fo = np.zeros(len(off) + 1, np.int64)
+        lib().afe_batch_frame_offsets(self._h, fo.ctypes.data_as(i64p))
+        self.frame_offsets, self.sample_offsets, self.sample_lengths = fo, off, ln
+        self.pcm_extent = int((off + ln).max()) if len(off) else 0
+        return int(total.value)
+
+    def plan_segments(self, sample_offsets, sample_lengths, first_frame, n_frames):
+        """Segments of longer streams: entry u outputs the rows of its frames [first_frame[u], first_frame[u] + n_frames[u])."""
+        off = np.ascontiguousarray(sample_offsets, np.int64)
+        ln = np.ascontiguousarray(sample_lengths, np.int64)
+        ff = np.ascontiguousarray(first_frame, np.int32)
+        nf = np.ascontiguousarray(n_frames, np.int32)
+        total = C.c_longlong(0)
+        i64p, ip = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+        _check(lib().afe_batch_plan_segments(self._h, off.ctypes.data_as(i64p), ln.ctypes.data_as(i64p), ff.ctypes.data_as(ip),
+                                             nf.ctypes.data_as(ip), len(off), C.byref(total)))
         fo = np.zeros(len(off) + 1, np.int64)
         lib().afe_batch_frame_offsets(self._h, fo.ctypes.data_as(i64p))
         self.frame_offsets, self.sample_offsets, self.sample_lengths = fo, off, ln

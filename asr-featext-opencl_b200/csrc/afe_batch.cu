@@ -595,7 +595,26 @@ int afe_batch_set_stream(afe_batch *b, void *cuda_stream)
     return 0;
 }
 
+static int plan_impl(afe_batch *b, const int64_t *off, const int64_t *len, const int *seg_first, const int *seg_rows, int n_utts,
+                     int64_t *total_frames);
+
 int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_utts, int64_t *total_frames)
+{
+    return plan_impl(b, off, len, nullptr, nullptr, n_utts, total_frames);
+}
+
+// Segments of longer streams (time sharding): entry u covers the samples [off, off + len) = T frames of context and
+// produces only the rows of its frames [first_frame[u], first_frame[u] + n_frames[u]); the frames in front of / behind that range
+// are real context for the deltas (no edge replication except where the segment touches the end of its sample range).
+int afe_batch_plan_segments(afe_batch *b, const int64_t *off, const int64_t *len, const int *first_frame, const int *n_frames,
+                            int n_segments, int64_t *total_frames)
+{
+    if (!first_frame || !n_frames) return fail("plan_segments: null segment arrays");
+    return plan_impl(b, off, len, first_frame, n_frames, n_segments, total_frames);
+}
+
+static int plan_impl(afe_batch *b, const int64_t *off, const int64_t *len, const int *seg_first, const int *seg_rows, int n_utts,
+                     int64_t *total_frames)
 {
     return guarded([&] {
         const Derived &d = b->d;
@@ -614,6 +633,8 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
         std::vector<int> tile_begin;
         std::vector<double> counts;
         const bool corpus = b->scope == AFE_STATS_CORPUS;
+        if (seg_first && d.p.norm != AFE_NORM_NONE && !corpus)
+            throw Error("plan_segments: normalisation over segments needs the CORPUS statistics scope");
         bool aligned = d.S % 8 == 0;
         double corpus_count = 0;
         // Wave balancing for small batches (a single long stream, a handful of files): with fewer than ~8 waves of CTAs the
@@ -650,12 +671,14 @@ int afe_batch_plan(afe_batch *b, const int64_t *off, const int64_t *len, int n_u
             // exact count (the extra frame would lie outside the utterance)
             const int T = std::min(afe_estimated_window_count((int)n, d.W, d.S), (int)std::max<int64_t>(0, (n - (d.W - d.S)) / d.S));
             if (T <= 2 * d.D || T < 1) throw Error("Can't process data, window count is too small"); // segmentercpu.cpp:65-66
-            b->frame_off[u + 1] = b->frame_off[u] + T;
+            const int t_first = seg_first ? seg_first[u] : 0, rows = seg_rows ? seg_rows[u] : T;
+            if (t_first < 0 || rows < 1 || t_first + rows > T) throw Error("plan_segments: segment outside its frames");
+            b->frame_off[u + 1] = b->frame_off[u] + rows;
             b->h_tile_begin[u] = (int)tiles.size();
             if (!corpus) tile_begin.push_back((int)tiles.size());
-            const int ntile = eng.plan_rows(tiles, off[u], b->frame_off[u], T, 0, T, corpus ? 0 : u, nout_cap);
+            const int ntile = eng.plan_rows(tiles, off[u], b->frame_off[u] - t_first, T, t_first, rows, corpus ? 0 : u, nout_cap);
             b->max_tiles_per_utt = std::max(b->max_tiles_per_utt, ntile);
-            const double cnt = !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
+            const double cnt = seg_first ? rows : !d.p.norm_after_dyn ? T : (b->scope == AFE_STATS_REFERENCE_BLOCK ? T - d.D : T);
             if (corpus) corpus_count += cnt; else counts.push_back(cnt);
         }
         if (corpus) { tile_begin.push_back(0); counts.push_back(corpus_count); }

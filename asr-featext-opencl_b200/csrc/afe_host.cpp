@@ -192,4 +192,25 @@ int afe_shard_utterances(const int64_t *len, int n_utts, int n_ranks, int *start
     });
 }
 
+// Time sharding of ONE stream over ranks: rank r produces the frames [first[r], first[r] + count[r]) and needs the
+// samples [sample_begin[r], sample_begin[r] + sample_count[r]), i.e. its frames plus D frames of context on each side
+// (the (W - S) + 2 D S sample halo of segmentercpu.cpp:69-73, 90-92). local_first[r] = index of its first frame inside that range.
+int afe_shard_stream(int64_t total_samples, int window_size, int shift, int delta_frames, int n_ranks, int64_t *sample_begin,
+                     int64_t *sample_count, int64_t *first, int *count, int *local_first)
+{
+    return guarded([&] {
+        if (n_ranks < 1 || window_size < 2 || shift < 1 || delta_frames < 0) throw Error("shard_stream: invalid arguments");
+        const int64_t T = total_samples >= window_size ? (total_samples - (window_size - shift)) / shift : 0;
+        if (T < (int64_t)n_ranks * (2 * delta_frames + 1)) throw Error("shard_stream: stream too short for this many ranks");
+        for (int r = 0; r < n_ranks; r++) {
+            const int64_t f0 = T * r / n_ranks, f1 = T * (r + 1) / n_ranks;
+            const int64_t c0 = std::max<int64_t>(0, f0 - delta_frames), c1 = std::min<int64_t>(T, f1 + delta_frames);
+            first[r] = f0; count[r] = (int)(f1 - f0);
+            local_first[r] = (int)(f0 - c0);
+            sample_begin[r] = c0 * shift;
+            sample_count[r] = (c1 - c0 - 1) * shift + window_size;
+        }
+    });
+}
+
 } // extern "C"

@@ -198,6 +198,11 @@ int afe_batch_set_stream(afe_batch *b, void *cuda_stream);
  * plain-load path is used. Builds the tile table and uploads it. total_frames receives sum of T. */
 int afe_batch_plan(afe_batch *b, const int64_t *sample_offsets, const int64_t *sample_lengths, int n_utts,
                    int64_t *total_frames);
+/* Segments of longer streams (time sharding, f4): entry u covers the samples [offset, offset + length) = T frames and produces only
+ * the rows of its frames [first_frame[u], first_frame[u] + n_frames[u]); frames outside that range are real delta context.
+ * Normalisation over segments needs the AFE_STATS_CORPUS scope (extract_device -> corpus_stats -> allreduce -> normalize_device). */
+int afe_batch_plan_segments(afe_batch *b, const int64_t *sample_offsets, const int64_t *sample_lengths, const int *first_frame,
+                            const int *n_frames, int n_segments, int64_t *total_frames);
 /* HOST int64[n_utts+1] first output row of each utterance */
 int afe_batch_frame_offsets(const afe_batch *b, int64_t *frame_offsets);
 int afe_batch_num_tiles(const afe_batch *b);
@@ -228,6 +233,13 @@ int afe_batch_run_host(afe_batch *b, const int16_t *h_pcm, float *h_out);
 int afe_cmvn_finalize_host(int norm_type, int width, const double *stats, float *mean, float *scale);
 /* contiguous utterance ranges balanced by samples: rank r owns utterances [starts[r], starts[r+1]); starts[n_ranks+1] */
 int afe_shard_utterances(const int64_t *sample_lengths, int n_utts, int n_ranks, int *starts);
+
+/* One stream over n_ranks GPUs by time: rank r produces the frames [first[r], first[r] + count[r]) from the samples
+ * [sample_begin[r], sample_begin[r] + sample_count[r]) (its frames + delta_frames of context per side, the reference's
+ * (W - S) + 2 D S carry-over, segmentercpu.cpp:69-73,90-92); local_first[r] is its first frame inside that sample range.
+ * Feed each rank's range to afe_batch_plan_segments; corpus scope + afe_normalizer_allreduce give stream-level CMN / CVN. */
+int afe_shard_stream(int64_t total_samples, int window_size, int shift, int delta_frames, int n_ranks, int64_t *sample_begin,
+                     int64_t *sample_count, int64_t *first, int *count, int *local_first);
 
 /* NCCL plumbing (libnccl is dlopen'ed; these fail loudly if it is missing). unique id = 128 bytes. */
 int afe_nccl_get_unique_id(void *id128);

@@ -718,3 +718,124 @@ def test_corpus_cmvn_nccl_two_gpus_equal_one():
     np.testing.assert_allclose(m0[:2 * w], rec[:2 * w], rtol=1e-13)
     np.testing.assert_array_equal(m0[2 * w + 1:], rec[2 * w + 1:])
     np.testing.assert_allclose(two, one, rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- f4: one stream, sharded by time
+def _run_stream_shard(p, x, sh, r, device=0, merged=None):
+    """Rank r of a time-sharded stream on `device`: raw rows, record, (normalised rows when `merged` is given)."""
+    b = afe.BatchMfcc(to_afe_params(p, BIG), device, stats_scope=afe.STATS_CORPUS)
+    seg = np.ascontiguousarray(x[sh["sample_begin"][r]:sh["sample_begin"][r] + sh["sample_count"][r]])
+    pcm, offs, lens = afe.pack_utterances([seg])
+    total = b.plan_segments(offs, lens, [sh["local_first"][r]], [sh["count"][r]])
+    assert total == sh["count"][r]
+    w = ol.width_of(p)
+    d_pcm = afe.DeviceBuffer(pcm.nbytes + 64, device); d_pcm.upload(pcm)
+    d_out = afe.DeviceBuffer(total * w * 4, device)
+    b.extract_device(d_pcm.ptr.value, d_out.ptr.value)
+    rec = None
+    if p["norm"]:
+        b.corpus_stats(); b.synchronize()
+        rec = b.corpus_record()
+        if merged is not None:
+            b.set_corpus_stats(merged)
+            b.normalize_device(d_out.ptr.value)
+    b.synchronize()
+    out = d_out.download((total, w), np.float32)
+    b.close(); d_pcm.free(); d_out.free()
+    return out, rec
+
+
+@pytest.mark.parametrize("norm", ["none", "cmn", "cvn"])
+def test_stream_time_sharded_equals_whole_stream(oracle, norm):
+    """ONE stream cut by time into 3 'ranks' (afe_shard_stream: frames + D frames of real context per side),
+    records merged like the all-reduce merges them. Without normalisation the rows are BITWISE those of the whole stream on one
+    GPU (frames do not depend on the cut); with stream-level CMN / CVN they agree to a rounding of the statistics, and both
+    match the reference's CPU classes (which see the stream in one block)."""
+    x = np.concatenate([load_pcm()["a5"], load_pcm()["a3"], load_pcm()["a0001"]])      # 47.6 s of speech
+    p = ol.default_params(norm=norm, dyn="acc")
+    whole = run_batch(p, [x], stats_scope=afe.STATS_UTTERANCE)[0]                      # statistics over all rows, no Q1
+    sh = afe.shard_stream(len(x), 400, 160, 6, 3)
+    parts = [_run_stream_shard(p, x, sh, r) for r in range(3)]
+    if norm == "none":
+        np.testing.assert_array_equal(np.concatenate([o for o, _ in parts]), whole)
+    else:
+        w = 39
+        recs = [rec for _, rec in parts]
+        merged = np.concatenate([sum(r[:2 * w + 1] for r in recs), np.minimum.reduce([r[2 * w + 1:3 * w + 1] for r in recs]),
+                                 np.maximum.reduce([r[3 * w + 1:] for r in recs])])
+        assert merged[2 * w] == len(whole)
+        got = np.concatenate([_run_stream_shard(p, x, sh, r, merged=merged)[0] for r in range(3)])
+        np.testing.assert_allclose(got, whole, rtol=0, atol=2e-6 if norm == "cmn" else 2e-5)
+    # and the whole-stream rows are the reference's (two set_input calls: no Q1; statistics over T - D rows there -> compare raw)
+    if norm == "none":
+        assert_close(whole, oracle_extract(oracle, p, [np.concatenate([x, np.zeros(3, np.int16)])], 0)[0], p, "whole stream")
+
+
+def _stream_shard_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import afe_loader, oracle_lib as ol
+    from common import synth_utterances
+    afe = afe_loader.load()
+    try:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        p = ol.default_params(window_size=200, shift=80, num_banks=20, sample_rate=8000.0, high_freq=4000.0, dyn="acc", norm="cmn")
+        x = synth_utterances(1, 2_400_000, seed=91, sr=8000.0)[0]                      # 5 minutes at 8 kHz
+        sh = afe.shard_stream(len(x), 200, 80, 6, world)
+        idb = [None]
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            afe._check(afe.lib().afe_nccl_get_unique_id(raw))
+            idb = [bytes(raw.raw)]
+        dist.broadcast_object_list(idb, 0)
+        comm = C.c_void_p()
+        afe._check(afe.lib().afe_nccl_comm_init(idb[0], world, rank, rank, C.byref(comm)))
+        from common import to_afe_params
+        b = afe.BatchMfcc(to_afe_params(p, 1 << 22), rank, stats_scope=afe.STATS_CORPUS)
+        seg = np.ascontiguousarray(x[sh["sample_begin"][rank]:sh["sample_begin"][rank] + sh["sample_count"][rank]])
+        pcm, offs, lens = afe.pack_utterances([seg])
+        total = b.plan_segments(offs, lens, [sh["local_first"][rank]], [sh["count"][rank]])
+        d_pcm = afe.DeviceBuffer(pcm.nbytes + 64, rank); d_pcm.upload(pcm)
+        d_out = afe.DeviceBuffer(total * 39 * 4, rank)
+        b.extract_device(d_pcm.ptr.value, d_out.ptr.value)
+        b.corpus_stats()
+        b.allreduce(comm.value)
+        b.normalize_device(d_out.ptr.value)
+        b.synchronize()
+        out = d_out.download((total, 39), np.float32)
+        b.close(); d_pcm.free(); d_out.free()
+        afe.lib().afe_nccl_comm_destroy(comm)
+        q.put((rank, out))
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put((rank, "error", repr(e)))
+
+
+def test_stream_time_sharded_nccl_two_gpus():
+    """f4 on hardware: a 5-minute 8 kHz stream cut in two, one half per GPU, stream-level CMN through afe_normalizer_allreduce
+    == the whole stream on one GPU within 1e-6. Skipped unless >= 2 GPUs are visible."""
+    if afe.lib().afe_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stream_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for pr in procs:
+        pr.join(60)
+    for r in res:
+        assert r[1] is not None and not (isinstance(r[1], str) and r[1] == "error"), r
+    res.sort(key=lambda r: r[0])
+    p = ol.default_params(window_size=200, shift=80, num_banks=20, sample_rate=8000.0, high_freq=4000.0, dyn="acc", norm="cmn")
+    x = synth_utterances(1, 2_400_000, seed=91, sr=8000.0)[0]
+    whole = run_batch(p, [x], stats_scope=afe.STATS_UTTERANCE)[0]
+    np.testing.assert_allclose(np.concatenate([res[0][1], res[1][1]]), whole, rtol=0, atol=1e-6)

@@ -142,3 +142,25 @@ def test_numpy_oracle_preemphasis_zero_is_identity():
     a, b = oracle_np.mfcc(pcm, p), oracle_np.mfcc(pcm, dict(p, preemphasis=0.0))
     np.testing.assert_array_equal(a, b)
     assert np.abs(oracle_np.mfcc(pcm, dict(p, preemphasis=0.97)) - a).max() > 0.1
+
+
+def test_shard_stream_covers_every_frame_once_with_the_reference_halo():
+    """afe_shard_stream (f4): contiguous frame ranges, each rank's sample range = its frames + D frames of context per side,
+    i.e. the (W - S) + 2 D S carry-over of segmentercpu.cpp:69-73,90-92 around interior cuts."""
+    for total, W, S, D, n in ((28_800_000, 200, 80, 6, 8), (81_000, 400, 160, 6, 3), (160_000, 400, 160, 0, 4), (54_682, 400, 160, 2, 2)):
+        sh = afe.shard_stream(total, W, S, D, n)
+        T = (total - (W - S)) // S
+        assert sh["first"][0] == 0 and int(sh["first"][-1] + sh["count"][-1]) == T
+        assert np.all(sh["first"][1:] == sh["first"][:-1] + sh["count"][:-1])            # contiguous, no overlap
+        for r in range(n):
+            c0 = max(0, sh["first"][r] - D)
+            c1 = min(T, sh["first"][r] + sh["count"][r] + D)
+            assert sh["sample_begin"][r] == c0 * S and sh["local_first"][r] == sh["first"][r] - c0
+            assert sh["sample_count"][r] == (c1 - c0 - 1) * S + W
+            assert sh["sample_begin"][r] + sh["sample_count"][r] <= total
+            assert afe.estimated_window_count(int(sh["sample_count"][r]), W, S) == c1 - c0
+        if n > 1:   # two neighbours share exactly (W - S) + 2 D S samples
+            overlap = sh["sample_begin"][0] + sh["sample_count"][0] - sh["sample_begin"][1]
+            assert overlap == (W - S) + 2 * D * S
+    with pytest.raises(afe.AfeError, match="too short"):
+        afe.shard_stream(4000, 400, 160, 6, 4)
