@@ -151,7 +151,7 @@ void count_launch(int n) { g_launches.fetch_add(n); }
 // ------------------------------------------------------------------------------------------------ K1 launch table
 #define AFE_DECL_INST(k) cudaError_t fused_launch_##k(const FusedLaunch &); int fused_max_clusters_##k(const FusedLaunch &);
 #define AFE_FOR_EACH_INST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) \
-    X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29)
+    X(18) X(19) X(20) X(21) X(22) X(23)
 AFE_FOR_EACH_INST(AFE_DECL_INST)
 #undef AFE_DECL_INST
 
@@ -186,29 +186,9 @@ std::string fused_unsupported_reason(const Derived &d)
     return "";
 }
 
-// The mel shape (afe_fused.cuh) whose fixed group counts cover this filterbank, or 0. A shape fits when the kernel it belongs to
-// is the one this parameter set runs (FFT size, filters per warp, pruned first FFT layer), every filter needs at most G[k]
-// 4-bin groups from its first group on, and no slot reads past the zeroed pad behind a magnitude row.
-static int pick_mel_shape(const Derived &d, const std::vector<int> &edges, bool pruned)
-{
-    if (!pruned) return 0;
-    const int kf = (d.nb + 7) / 8;
-    for (int shape = 1; shape <= kMelShapes; shape++) {
-        if (mel_shape_n2(shape) != d.N2 || mel_shape_kf(shape) != (kf <= 3 ? 3 : kf <= 5 ? 5 : 8)) continue;
-        bool ok = true;
-        for (int b = 0; b < d.nb && ok; b++) {
-            const int s4 = edges[b] & ~3, need = std::max(1, (edges[b + 2] - s4 + 3) / 4), g = mel_shape_g(shape, b / 8);
-            ok = need <= g && s4 + 4 * g <= kMagStride + 16;
-        }
-        if (ok) return shape;
-    }
-    return 0;
-}
-
 // Mel weights + DCT matrix as a by-value kernel parameter (constant bank). Per filter b: bins [edges[b], edges[b+2]) with
 // weights filters[b%2][bin] — the per-filter form of the reference's two-running-sums sweep (mfcccpu.cpp:192-220).
-// Returns the mel shape the tables are laid out for (0: the generic lists).
-static int build_mel_const(const Derived &d, float alpha, bool pruned, bool allow_shapes, MelConst &mc)
+static void build_mel_const(const Derived &d, float alpha, MelConst &mc)
 {
     std::vector<int> edges; std::vector<float> filters, dct;
     build_filters(d, alpha, edges, filters);
@@ -216,32 +196,25 @@ static int build_mel_const(const Derived &d, float alpha, bool pruned, bool allo
         if (edges[i + 1] < edges[i]) throw Error("mel filter edges are not monotonic");
     if (edges.front() < 0 || edges.back() > d.M) throw Error("mel filterbank exceeds the Nyquist bin (check low_freq/high_freq)");
     memset(&mc, 0, sizeof mc);
-    const int shape = allow_shapes ? pick_mel_shape(d, edges, pruned) : 0;
     int off4 = 0;
     const float scale = 0.5f / (float)d.N2; // the kernel stores |2X|; scaling by a power of two commutes with rounding
     for (int w = 0; w < 8; w++) {           // warp class w owns the filters w, w + 8, ...: their lists are contiguous
         mc.wstart[w] = (short)off4;
         for (int b = w; b < d.nb; b += 8) {
             const int j0 = edges[b], j1 = edges[b + 2], s4 = j0 & ~3, n8 = std::max(1, (j1 - s4 + 7) / 8);
+            if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
             if (s4 + 8 * n8 > kMagStride + 16) throw Error("mel filter too wide for the fused kernel");
             mc.desc[b] = (s4 / 4) | (n8 << 16);
-            float *wt;
-            if (shape) // fixed layout: warp class w, slot k = b / 8, G[k] groups of 4 bins from s4 on
-                wt = reinterpret_cast<float *>(mc.wl4 + w * mel_shape_sum(shape) + mel_shape_prefix(shape, b / 8));
-            else {
-                if (off4 + 2 * n8 > kMaxWl4) throw Error("mel weight list exceeds the kernel-parameter budget");
-                wt = reinterpret_cast<float *>(mc.wl4 + off4);
-                off4 += 2 * n8;
-            }
+            float *wt = reinterpret_cast<float *>(mc.wl4 + off4);
             for (int j = j0; j < j1; j++) wt[j - s4] = filters[(size_t)(b % 2) * d.N2 + j] * scale;
+            off4 += 2 * n8;
         }
     }
     if (d.C > 0) {
         build_dct(d, dct);
-        for (int k = 0; k < d.nb; k++) // row of filter k = w + 8 * slot at index 8 * w + slot
-            for (int j = 0; j < d.dct_len; j++) reinterpret_cast<float *>(mc.dct4[8 * (k % 8) + k / 8])[j] = dct[(size_t)k * d.dct_len + j];
+        for (int k = 0; k < d.nb; k++)
+            for (int j = 0; j < d.dct_len; j++) reinterpret_cast<float *>(mc.dct4[k])[j] = dct[(size_t)k * d.dct_len + j];
     }
-    return shape;
 }
 
 FusedEngine::FusedEngine(const Derived &dd, int dev) : d(dd), device(dev)
@@ -273,22 +246,14 @@ void FusedEngine::set_window(const float *window, cudaStream_t st)
 }
 void FusedEngine::ensure_mel(float alpha)
 {
-    if (mc_alpha != alpha || mc_shapes != allow_shapes) {
-        shape = build_mel_const(d, alpha, pruned, allow_shapes, mc);
-        mc_alpha = alpha; mc_shapes = allow_shapes;
-    }
-}
-int FusedEngine::variant_key(float pre_coef) const
-{
-    if (shape > 0) return 24 + 2 * (shape - 1) + (pre_coef != 0.f ? 1 : 0);
-    return key + (pre_coef != 0.f ? 12 : 0);
+    if (mc_alpha != alpha) { build_mel_const(d, alpha, mc); mc_alpha = alpha; }
 }
 std::string FusedEngine::kernel_label() const
 {
     const int kf = (d.nb + 7) / 8;
     char buf[96];
-    snprintf(buf, sizeof buf, "k_fused_mfcc<%d,%d,8,%d,%s,%d>", d.N2, pruned ? 13 : 16, kf <= 3 ? 3 : kf <= 5 ? 5 : 8,
-             pre != 0.f ? "true" : "false", shape);
+    snprintf(buf, sizeof buf, "k_fused_mfcc<%d,%d,8,%d,%s>", d.N2, pruned ? 13 : 16, kf <= 3 ? 3 : kf <= 5 ? 5 : 8,
+             pre != 0.f ? "true" : "false");
     return buf;
 }
 
@@ -365,7 +330,7 @@ bool FusedEngine::cluster_schedulable(int cluster, const FusedArgs &a, cudaStrea
     if (cluster < 1 || cluster > 4) return false;
     if (cluster_probe[cluster] < 0) {
         FusedLaunch fl{a, L, &mc, cluster, cluster, st};
-        const int n = fused_variant_max_clusters(variant_key(a.pre), fl);
+        const int n = fused_variant_max_clusters(key, fl); // same footprint with and without pre-emphasis
         cluster_probe[cluster] = n > 0 ? n : 0;
     }
     return cluster_probe[cluster] > 0;
@@ -375,7 +340,7 @@ void FusedEngine::launch(const FusedArgs &a, int grid, int cluster, cudaStream_t
 {
     if (!window_set) throw Error("set_window must be called before running");
     FusedLaunch fl{a, L, &mc, grid, cluster, st};
-    const cudaError_t e = launch_fused_variant(variant_key(a.pre), fl);
+    const cudaError_t e = launch_fused_variant(key + (a.pre != 0.f ? 12 : 0), fl);
     if (e != cudaSuccess) {
         cudaGetLastError();
         throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at k_fused_mfcc launch" + (cluster > 0 ? " (clustered)" : ""));
@@ -470,7 +435,6 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
     if (t1 <= t0) return;
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
     FusedEngine &eng = *b->eng;
-    eng.allow_shapes = !(b->flags & AFE_BATCH_GENERIC_MEL);
     eng.ensure_mel(b->alpha);
     const Derived &d = b->d;
     const bool want_stats = d.p.norm != AFE_NORM_NONE;
@@ -773,13 +737,8 @@ int afe_batch_num_tiles(const afe_batch *b) { return b->n_tiles; }
 int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
 const char *afe_batch_kernel_name(const afe_batch *b)
 {
-    // the instantiation the next run launches (the mel tables follow alpha and AFE_BATCH_GENERIC_MEL)
     static thread_local std::string name;
-    try {
-        b->eng->allow_shapes = !(b->flags & AFE_BATCH_GENERIC_MEL);
-        b->eng->ensure_mel(b->alpha);
-        name = b->eng->kernel_label();
-    } catch (...) { name = "k_fused_mfcc"; }
+    name = b->eng ? b->eng->kernel_label() : "k_fused_mfcc";
     return name.c_str();
 }
 afe_normalizer *afe_batch_normalizer(afe_batch *b) { return b->cnorm; }

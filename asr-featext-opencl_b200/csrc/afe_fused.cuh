@@ -61,42 +61,11 @@ struct MelConst {
     float4 wl4[kMaxWl4];         // weights of filter b: 2*n8[b] float4 = bins 4*fchunk[b] + 8*i + {0..7}, i < n8[b]. The lists
                                  // of the filters of one warp class (b = w, w + 8, w + 16, ...) are CONTIGUOUS from
                                  // wstart[w], in that order, so phase 2 walks them with one running offset. The weights
-                                 // carry the 0.5/N2 magnitude scale (an exact power of two), see fft_frame_mag.
-                                 // Shape-specialised kernels (SHAPE > 0, below) read a FIXED layout instead: warp class w,
-                                 // slot k (filter w + 8k), group i < G[k]: wl4[w * sum(G) + prefix(k) + i] = bins
-                                 // 4*fchunk[b] + 4*i + {0..3}, zero past the filter's end
-    float4 dct4[kMaxBanks][4];   // row of filter b = w + 8k at index 8*w + k ([16] columns, zero padded): one warp class's rows
-                                 // are contiguous and 512-byte aligned, which lets ptxas prove 128-bit constant loads
+                                 // carry the 0.5/N2 magnitude scale (an exact power of two), see fft_frame_mag
+    float4 dct4[kMaxBanks][4];   // [nb][16]
     int desc[kMaxBanks];         // fchunk[b] (first 4-bin chunk = edges[b] / 4; leading weights are zero) | n8[b] << 16
     short wstart[8];             // first float4 of warp class w (8 warps per CTA)
 };
-
-// ---- mel "shapes": phase 2 with every trip count known at compile time. The generic kernel (SHAPE 0) walks each filter's
-// weight list with a run-time chunk count: per 8 bins it issues 4 FFMA2 and 12 instructions of uniform address arithmetic,
-// loop control and indexed 64-bit constant loads, and it waits on that serial chain (profiles/r02_a: 118.8 warp-instructions
-// per frame, 34 % short-scoreboard stalls). A shape fixes, per filter slot k (the filters 8k .. 8k+7, one per warp), the
-// number G[k] of 4-bin groups every warp reads; filters that need fewer groups meet zero weights. The code is then straight
-// line: one LDS.128 + one LDCU.128 (static offset from one uniform base) per two FFMA2. The host picks the first shape
-// that covers the filterbank at hand (FusedEngine::ensure_mel); banks no shape covers run SHAPE 0. The sums are the same
-// operations in the same order, so both paths give the same bits (tests/test_gpu_parity.py).
-constexpr int kMelShapes = 3;
-__host__ __device__ constexpr int mel_shape_kf(int shape) { return shape == 1 ? 5 : 3; }
-__host__ __device__ constexpr int mel_shape_n2(int shape) { return shape == 2 ? 256 : 512; }
-__host__ __device__ constexpr int mel_shape_g(int shape, int k)
-{
-    // 1: 40 filters 64 Hz - 8 kHz at 16 kHz / 512 points (BASELINE configs[2], [3]);  2: 20 filters up to 4 kHz at 8 kHz / 256
-    // points (configs[4]);  3: 23 filters at 16 kHz / 512 points (the reference driver's default, configs[0], [1])
-    return shape == 1 ? (k == 0 ? 2 : k == 1 ? 3 : k == 2 ? 4 : k == 3 ? 6 : k == 4 ? 8 : 0)
-         : shape == 2 ? (k == 0 ? 3 : k == 1 ? 5 : k == 2 ? 6 : 0)
-         : shape == 3 ? (k == 0 ? 4 : k == 1 ? 7 : k == 2 ? 13 : 0) : 0;
-}
-__host__ __device__ constexpr int mel_shape_prefix(int shape, int k)
-{
-    int s = 0;
-    for (int i = 0; i < k; i++) s += mel_shape_g(shape, i);
-    return s;
-}
-__host__ __device__ constexpr int mel_shape_sum(int shape) { return mel_shape_prefix(shape, mel_shape_kf(shape)); }
 
 struct FusedArgs {
     const int16_t *pcm;
@@ -381,44 +350,6 @@ __device__ __forceinline__ void phase3_l3(const int KIND, const FusedArgs &a, co
 } // namespace dev
 
 namespace dev {
-// Phase 2 of a shape-specialised kernel, warp class W (filters W, W + 8, ...): mel sums and DCT with compile-time constant
-// addresses. Chains as in the generic loop: bins 0,1 of every 4-bin group feed acc0, bins 2,3 feed acc1, ascending bins.
-template <int SHAPE, int W, int KF>
-__device__ __forceinline__ void mel_sums_static(const MelConst &mc, uint32_t mrow_s, float (&es)[KF])
-{
-    uint32_t maddr[KF];
-#pragma unroll
-    for (int k = 0; k < KF; k++) maddr[k] = mrow_s + ((mc.desc[W + k * 8] & 0xffff) << 4);
-#pragma unroll
-    for (int k = 0; k < KF; k++) {
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
-#pragma unroll
-        for (int i = 0; i < mel_shape_g(SHAPE, k); i++) {
-            const float4 m = lds128(maddr[k] + 16 * i);
-            const float4 w = mc.wl4[W * mel_shape_sum(SHAPE) + mel_shape_prefix(SHAPE, k) + i];
-            acc0 = __ffma2_rn(make_float2(m.x, m.y), make_float2(w.x, w.y), acc0);
-            acc1 = __ffma2_rn(make_float2(m.z, m.w), make_float2(w.z, w.w), acc1);
-        }
-        const float2 t = __fadd2_rn(acc0, acc1);
-        es[k] = t.x + t.y;
-    }
-}
-template <int W, int KF> __device__ __forceinline__ void dct_static(const MelConst &mc, const float (&es)[KF], float2 (&cep)[8])
-{
-#pragma unroll
-    for (int k = 0; k < KF; k++) {
-        const float2 e2 = make_float2(es[k], es[k]);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-            const float4 d4 = mc.dct4[8 * W + k][c4];
-            cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
-            cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
-        }
-    }
-}
-} // namespace dev
-
-namespace dev {
 __device__ __forceinline__ Tile load_tile(const FusedArgs &a, int idx)
 {
     if (a.blk_ntiles == 0) return a.tiles[idx];
@@ -593,9 +524,8 @@ __device__ __forceinline__ void normalise_role(const FusedArgs &a, const Tile tl
 } // namespace dev
 
 // KF = filters per warp in phase 2 (ceil(num_banks / WARPS), rounded up to 3, 5 or 8): the phase is unrolled KF times,
-// so a tight bound keeps the round loop inside the instruction cache. SHAPE > 0: the mel sums of phase 2 are straight-line
-// code for that shape (mel_shape_g), KF == mel_shape_kf(SHAPE).
-template <int N2, int NZ, int kFusedWarps, int KF, bool PRE, int SHAPE = 0>
+// so a tight bound keeps the round loop inside the instruction cache.
+template <int N2, int NZ, int kFusedWarps, int KF, bool PRE>
 __global__ void __launch_bounds__(32 * kFusedWarps, 2)
 k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelConst mc)
 {
@@ -713,65 +643,47 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
         //      Three unrolled passes over the warp's <= KF filters - sums, logs, DCT - so that the independent filters'
         //      long dependency chains (accumulation, logf) interleave instead of running back to back.
         #ifdef AFE_DEVTOOLS
-        if ((SHAPE > 0 || lane < nfr) && !(a.debug_skip & 2)) {
+        if (lane < nfr && !(a.debug_skip & 2)) {
 #else
-        // SHAPE > 0: no divergence (the uniform datapath, i.e. LDCU.128 straight into the FFMA2 operand, needs a converged
-        // warp): lanes without a live frame work on a stale but finite magnitude row and their results are never read
-        if (SHAPE > 0 || lane < nfr) {
+        if (lane < nfr) {
 #endif
             float es[KF];
-            if constexpr (SHAPE > 0) {
-                static_assert(SHAPE <= kMelShapes && KF == mel_shape_kf(SHAPE) && N2 == mel_shape_n2(SHAPE), "shape / kernel mismatch");
-                // straight-line sums, one copy of the code per warp class (dev::mel_sums_static): every constant address is
-                // an immediate, which is what makes ptxas use 128-bit uniform loads (LDCU.128 -> FFMA2 operand)
-                switch (warp) {
-                case 0: dev::mel_sums_static<SHAPE, 0, KF>(mc, mrow_s, es); break;
-                case 1: dev::mel_sums_static<SHAPE, 1, KF>(mc, mrow_s, es); break;
-                case 2: dev::mel_sums_static<SHAPE, 2, KF>(mc, mrow_s, es); break;
-                case 3: dev::mel_sums_static<SHAPE, 3, KF>(mc, mrow_s, es); break;
-                case 4: dev::mel_sums_static<SHAPE, 4, KF>(mc, mrow_s, es); break;
-                case 5: dev::mel_sums_static<SHAPE, 5, KF>(mc, mrow_s, es); break;
-                case 6: dev::mel_sums_static<SHAPE, 6, KF>(mc, mrow_s, es); break;
-                default: dev::mel_sums_static<SHAPE, 7, KF>(mc, mrow_s, es); break;
-                }
-            } else {
-                int woff = mc.wstart[warp]; // running float4 offset into this warp class's weight lists (uniform)
-                // the first 8-bin chunk of every filter of this warp is loaded up front (2*KF independent 128-bit loads in
-                // flight): 40 of the 89 chunks of the 40-filter bank, so most filters never wait for shared memory
-                int dsc[KF];
-                float4 mf0[KF], mf1[KF];
+            int woff = mc.wstart[warp]; // running float4 offset into this warp class's weight lists (uniform)
+            // the first 8-bin chunk of every filter of this warp is loaded up front (2*KF independent 128-bit loads in
+            // flight): 40 of the 89 chunks of the 40-filter bank, so most filters never wait for shared memory
+            int dsc[KF];
+            float4 mf0[KF], mf1[KF];
 #pragma unroll
-                for (int k = 0; k < KF; k++) {
-                    const int b = warp + k * kFusedWarps;
-                    dsc[k] = b < a.nb ? mc.desc[b] : 0;
-                    const uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
-                    mf0[k] = dev::lds128(maddr);
-                    mf1[k] = dev::lds128(maddr + 16);
-                }
+            for (int k = 0; k < KF; k++) {
+                const int b = warp + k * kFusedWarps;
+                dsc[k] = b < a.nb ? mc.desc[b] : 0;
+                const uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
+                mf0[k] = dev::lds128(maddr);
+                mf1[k] = dev::lds128(maddr + 16);
+            }
 #pragma unroll
-                for (int k = 0; k < KF; k++) {
-                    // four chains (bins 0,1 | 2,3 of every 4-bin group) in two register pairs: FFMA2, ascending bins in each
-                    float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
-                    int n8 = dsc[k] >> 16;       // 0 for a slot past num_banks (warp uniform), else >= 1
-                    if (n8 > 0) {
-                        uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
-                        float4 m0 = mf0[k], m1 = mf1[k];
-                        for (;;) {
-                            const float4 w0 = mc.wl4[woff], w1 = mc.wl4[woff + 1];
-                            acc0 = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc0);
-                            acc1 = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc1);
-                            acc0 = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc0);
-                            acc1 = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc1);
-                            woff += 2;
-                            if (--n8 == 0) break;
-                            maddr += 32;
-                            m0 = dev::lds128(maddr);
-                            m1 = dev::lds128(maddr + 16);
-                        }
+            for (int k = 0; k < KF; k++) {
+                // four chains (bins 0,1 | 2,3 of every 4-bin group) in two register pairs: FFMA2, ascending bins in each
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0;
+                int n8 = dsc[k] >> 16;       // 0 for a slot past num_banks (warp uniform), else >= 1
+                if (n8 > 0) {
+                    uint32_t maddr = mrow_s + ((dsc[k] & 0xffff) << 4);
+                    float4 m0 = mf0[k], m1 = mf1[k];
+                    for (;;) {
+                        const float4 w0 = mc.wl4[woff], w1 = mc.wl4[woff + 1];
+                        acc0 = __ffma2_rn(make_float2(m0.x, m0.y), make_float2(w0.x, w0.y), acc0);
+                        acc1 = __ffma2_rn(make_float2(m0.z, m0.w), make_float2(w0.z, w0.w), acc1);
+                        acc0 = __ffma2_rn(make_float2(m1.x, m1.y), make_float2(w1.x, w1.y), acc0);
+                        acc1 = __ffma2_rn(make_float2(m1.z, m1.w), make_float2(w1.z, w1.w), acc1);
+                        woff += 2;
+                        if (--n8 == 0) break;
+                        maddr += 32;
+                        m0 = dev::lds128(maddr);
+                        m1 = dev::lds128(maddr + 16);
                     }
-                    const float2 t = __fadd2_rn(acc0, acc1);
-                    es[k] = t.x + t.y;
                 }
+                const float2 t = __fadd2_rn(acc0, acc1);
+                es[k] = t.x + t.y;
             }
             // logs two at a time (packed); a filter slot past num_banks holds 0 -> log(1e-30), never used
 #pragma unroll
@@ -787,27 +699,15 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
                 // no branch on b < num_banks: the DCT rows of the slots past it are zero (MelConst is zero filled) and their
                 // es is the finite log(1e-30), so the straight-line code lets the constant loads run ahead of the FMAs
                 // (6.23 -> 6.15 ms)
-                if constexpr (SHAPE > 0) {
-                    switch (warp) {
-                    case 0: dev::dct_static<0, KF>(mc, es, cep); break;
-                    case 1: dev::dct_static<1, KF>(mc, es, cep); break;
-                    case 2: dev::dct_static<2, KF>(mc, es, cep); break;
-                    case 3: dev::dct_static<3, KF>(mc, es, cep); break;
-                    case 4: dev::dct_static<4, KF>(mc, es, cep); break;
-                    case 5: dev::dct_static<5, KF>(mc, es, cep); break;
-                    case 6: dev::dct_static<6, KF>(mc, es, cep); break;
-                    default: dev::dct_static<7, KF>(mc, es, cep); break;
-                    }
-                } else {
 #pragma unroll
-                    for (int k = 0; k < KF; k++) {
-                        const float2 e2 = make_float2(es[k], es[k]);
+                for (int k = 0; k < KF; k++) {
+                    const int b = warp + k * kFusedWarps;
+                    const float2 e2 = make_float2(es[k], es[k]);
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            const float4 d4 = mc.dct4[(warp << 3) + k][c4]; // row of filter warp + 8k
-                            cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
-                            cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
-                        }
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const float4 d4 = mc.dct4[b][c4];
+                        cep[2 * c4 + 0] = __ffma2_rn(e2, make_float2(d4.x, d4.y), cep[2 * c4 + 0]);
+                        cep[2 * c4 + 1] = __ffma2_rn(e2, make_float2(d4.z, d4.w), cep[2 * c4 + 1]);
                     }
                 }
                 // partial cepstra of this filter class -> the exchange tile of the warp that will sum column group c4
@@ -818,7 +718,7 @@ k_fused_mfcc(const FusedArgs a, const FusedSmem L, const __grid_constant__ MelCo
             } else {
 #pragma unroll
                 for (int k = 0; k < KF; k++)
-                    if (warp + k * kFusedWarps < a.nb && lane < nfr) s_cep[(f0 + lane) * cols + warp + k * kFusedWarps] = es[k];
+                    if (warp + k * kFusedWarps < a.nb) s_cep[(f0 + lane) * cols + warp + k * kFusedWarps] = es[k];
             }
         }
         __syncthreads(); // B: partial cepstra are complete; the magnitudes may be overwritten

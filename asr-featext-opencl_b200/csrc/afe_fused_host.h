@@ -18,8 +18,6 @@ struct FusedEngine {
     MelTables mel;               // window tables only (the mel weights travel in `mc`)
     MelConst mc;
     float mc_alpha = -1.f;
-    int shape = 0;               // mel shape `mc` is laid out for (afe_fused.cuh: mel_shape_g); 0 = generic lists
-    bool allow_shapes = true, mc_shapes = true; // allow_shapes = false forces the generic kernel (A-B tests)
     bool pruned = false;         // zero-padded window tail: the first FFT layer is pruned (NZ = 13)
     bool window_set = false;
     float pre = 0.f;             // pre-emphasis coefficient
@@ -34,8 +32,7 @@ struct FusedEngine {
 
     void set_window(const float *window, cudaStream_t st);
     void ensure_mel(float alpha);   // rebuilds the constant-bank tables when alpha changed (refresh_filters, mfcccpu.cpp:24-60)
-    int variant_key(float pre_coef) const; // instantiation of k_fused_mfcc for the tables at hand (afe_fused_launch.h)
-    std::string kernel_label() const;
+    std::string kernel_label() const; // the instantiation that runs, e.g. "k_fused_mfcc<512,13,8,5,false>"
     // Tiles for the output rows [t_first, t_first + n_out) of a sequence of T frames whose PCM starts at sample pcm_off;
     // output row of frame t = out_row0 + t. Appends to `tiles`; returns the number of tiles added.
     // nout_cap: largest tile (output frames), 0 = as large as the kernel's cepstra buffer allows (best throughput for big

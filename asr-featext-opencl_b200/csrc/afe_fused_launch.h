@@ -1,5 +1,5 @@
-// Launch interface of the fused kernel's instantiations. k_fused_mfcc<N2, NZ, 8, KF, PRE, SHAPE> is instantiated for 30
-// parameter sets, one per translation unit (afe_fused_inst.cu compiled with -DAFE_INST_KEY=0..29) so that they build in parallel.
+// Launch interface of the fused kernel's instantiations. k_fused_mfcc<N2, NZ, 8, KF, PRE> is instantiated for 24 parameter
+// sets, one per translation unit (afe_fused_inst.cu compiled with -DAFE_INST_KEY=0..23) so that they build in parallel.
 #pragma once
 #include "afe_fused.cuh"
 
@@ -14,9 +14,8 @@ struct FusedLaunch {
     cudaStream_t st;
 };
 
-// generic mel loop: key = (N2 == 512 ? 0 : 6) + (pruned first layer, NZ = 13 ? 0 : 3) + (KF: 3 -> 0, 5 -> 1, 8 -> 2) + (pre-emphasis ? 12 : 0)
-// mel shape s = 1..kMelShapes (pruned first layer only): key = 24 + 2 * (s - 1) + (pre-emphasis ? 1 : 0)
-constexpr int kFusedVariants = 24 + 2 * kMelShapes;
+// key = (N2 == 512 ? 0 : 6) + (pruned first layer, NZ = 13 ? 0 : 3) + (KF: 3 -> 0, 5 -> 1, 8 -> 2) + (pre-emphasis ? 12 : 0)
+constexpr int kFusedVariants = 24;
 cudaError_t launch_fused_variant(int key, const FusedLaunch &fl);
 // occupancy probe for the cluster path (cudaOccupancyMaxActiveClusters); < 0 on error
 int fused_variant_max_clusters(int key, const FusedLaunch &fl);

@@ -627,8 +627,7 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     cx.barrier, cx.max_over_ranks = barrier, max_over_ranks
-    cx.flags = (afe.BATCH_Q1_EXACT | (afe.BATCH_NO_TMA if args.no_tma else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0)
-                | (afe.BATCH_GENERIC_MEL if args.generic_mel else 0))
+    cx.flags = afe.BATCH_Q1_EXACT | (afe.BATCH_NO_TMA if args.no_tma else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0)
     cx.ap16 = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in params_dict().items() if k != "alpha"})
     # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
     cx.stream = torch.cuda.Stream(device=cx.dev)
@@ -772,7 +771,6 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to their GPU's NUMA node (A/B, N > 1)")
     ap.add_argument("--no-cluster", action="store_true", help="ticket-scheme normalisation instead of clusters + DSMEM (A/B)")
     ap.add_argument("--no-tma", action="store_true")
-    ap.add_argument("--generic-mel", action="store_true", help="generic mel loop instead of the shape-specialised kernel (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 / config-5 / stream-object extra blocks")

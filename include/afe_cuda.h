@@ -181,10 +181,8 @@ enum afe_batch_flags {
     AFE_BATCH_Q1_EXACT = 1,        /* reproduce the single-block flush quirk Q1 (statics of the last D rows) */
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
     AFE_BATCH_UNFUSED_NORM = 8,    /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
-    AFE_BATCH_NO_CLUSTER = 32,     /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
+    AFE_BATCH_NO_CLUSTER = 32      /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
                                       place via L2) instead of thread-block clusters + distributed shared memory (A-B test) */
-    AFE_BATCH_GENERIC_MEL = 64     /* run the generic mel loop even when a shape-specialised instantiation of the fused kernel
-                                      covers the filterbank (A-B test; both give the same bits) */
 };
 
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out);
@@ -209,7 +207,7 @@ int afe_batch_plan_segments(afe_batch *b, const int64_t *sample_offsets, const i
 int afe_batch_frame_offsets(const afe_batch *b, int64_t *frame_offsets);
 int afe_batch_num_tiles(const afe_batch *b);
 int afe_batch_kernel_launches(const afe_batch *b); /* kernels launched by the last run */
-const char *afe_batch_kernel_name(const afe_batch *b); /* the instantiation the next run launches, e.g. "k_fused_mfcc<512,13,8,5,false,1>" */
+const char *afe_batch_kernel_name(const afe_batch *b); /* the instantiation that runs, e.g. "k_fused_mfcc<512,13,8,5,false>" */
 /* d_pcm: DEVICE int16 buffer covering every [offset, offset+length) (+16 B slack after the last sample),
  * d_out: DEVICE float[total_frames][width]. Asynchronous on the handle's stream. */
 int afe_batch_run_device(afe_batch *b, const int16_t *d_pcm, float *d_out);

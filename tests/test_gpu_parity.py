@@ -282,31 +282,6 @@ def test_batch_is_deterministic_and_order_independent():
         np.testing.assert_array_equal(a[i], e[i])
 
 
-@pytest.mark.parametrize("cfg", [dict(num_banks=40), dict(num_banks=23), dict(num_banks=20, window_size=200, shift=80,
-                                                                              sample_rate=8000.0, high_freq=4000.0),
-                                 dict(num_banks=40, ceps_len=0, want_c0=0)])
-def test_batch_shape_specialised_mel_equals_generic_loop(cfg):
-    """The three filterbanks of BASELINE's configurations run an instantiation of the fused kernel whose mel sums are
-    straight-line code (mel shapes, afe_fused.cuh); AFE_BATCH_GENERIC_MEL forces the generic run-time loop. Same operations
-    in the same order: bitwise equal, with and without pre-emphasis, for cepstra and for log-mel (FBANK) output. A
-    warped filterbank (alpha != 1) that a shape still covers stays on the fast kernel, one it does not cover falls back."""
-    p = ol.default_params(norm="cmn", dyn="acc", **cfg)
-    utts = synth_utterances(12, 50000, seed=41, ragged=True)
-    for alpha in (1.0, 0.9, 1.12):
-        a = run_batch(p, utts, alpha=alpha)
-        b = run_batch(p, utts, alpha=alpha, flags=afe.BATCH_GENERIC_MEL)
-        for u, v in zip(a, b):
-            np.testing.assert_array_equal(u, v)
-    ap = to_afe_params(p, 1 << 22)
-    bm = afe.BatchMfcc(ap, 0)
-    try:
-        assert bm.kernel_name.endswith(",%d>" % {40: 1, 20: 2, 23: 3}[cfg["num_banks"]]), bm.kernel_name
-        bm.set_options(0, afe.BATCH_GENERIC_MEL)
-        assert bm.kernel_name.endswith(",0>"), bm.kernel_name
-    finally:
-        bm.close()
-
-
 @pytest.mark.parametrize("norm", ["cmn", "cvn", "minmax"])
 def test_batch_cluster_normalisation_equals_ticket_scheme(norm):
     """Fused normalisation inside a thread-block cluster (one cluster = the 1 or 2 tiles of an utterance, statistics
