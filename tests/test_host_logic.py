@@ -164,3 +164,32 @@ def test_shard_stream_covers_every_frame_once_with_the_reference_halo():
             assert overlap == (W - S) + 2 * D * S
     with pytest.raises(afe.AfeError, match="too short"):
         afe.shard_stream(4000, 400, 160, 6, 4)
+
+
+def test_documents_point_at_files_that_exist():
+    """DESIGN.md / INTEGRATION.md / README.md / profiles/README.md cite evidence and sources by path: every cited path that
+    names a tracked area of this repo must exist (a stale citation is a claim without evidence)."""
+    import re
+    root = ol.ROOT
+    areas = ("profiles/", "tools/", "tests/", "oracle/", "include/", "asr-featext-opencl_b200/")
+    missing = []
+    for doc in ("DESIGN.md", "INTEGRATION.md", "README.md", os.path.join("profiles", "README.md")):
+        text = open(os.path.join(root, doc)).read()
+        for m in re.finditer(r"`([A-Za-z0-9_./\-]+)`", text):
+            path = m.group(1)
+            if "*" in path or "…" in path or "..." in path:
+                continue
+            cands = [path]
+            if doc.startswith("profiles") and "/" not in path:
+                if not re.search(r"\.(json|jsonl|txt|csv)$", path):
+                    continue
+                cands = [os.path.join("profiles", path)]          # the index names its files without the directory
+            elif path.startswith(("csrc/", "host/")):
+                cands = [os.path.join("asr-featext-opencl_b200", path)]
+            if not cands[0].startswith(areas):
+                continue
+            if cands[0].startswith("oracle/_ref/") or cands[0].endswith((".so", "afe_extract", "afe_stream_bench", "tc_fft_proto")):
+                continue                                           # built artefacts, not tracked
+            if not os.path.exists(os.path.join(root, cands[0].rstrip("/"))):
+                missing.append((doc, path))
+    assert not missing, missing
