@@ -130,6 +130,10 @@ static void seg_frames(const port_seg *s, float *out, int frames) /* segmentercp
 static int seg_set_input(port_seg *s, const short *in, float *out, int samples, int *wc, int *wc_nd)
 {
     s->last_calc_flushed = s->flushed;
+    /* The reference copies without a bound check (segmentercpu.cpp:61,78): carry-over + block can exceed the buffer of
+     * window_limit * S + W - S samples (e.g. W > 2 S without deltas) and it overruns its heap. The port refuses instead. */
+    if ((size_t)samples + (s->flushed ? 0 : (size_t)s->remaining) > s->cap)
+        return fail("Can't process data, buffer is too small (the reference overruns its buffer here)");
     if (s->flushed) { /* first block of a stream: segmentercpu.cpp:59-75 */
         memcpy(s->carry, in, sizeof(short) * samples);
         *wc_nd = est_windows(samples, s->W, s->S);

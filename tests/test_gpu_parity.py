@@ -81,6 +81,18 @@ def test_stream_error_behaviour():
     m.close()
 
 
+def test_stream_refuses_where_the_reference_overruns_its_buffer():
+    """W > 2S without deltas: carry-over (W - S + leftover) + a full block exceeds the reference's buffer of
+    (est(limit) + 2) * S + W - S samples and SegmenterCPU::set_input overruns its heap (segmentercpu.cpp:41,76-78; found by
+    tools/fuzz_gpu.py, confirmed under AddressSanitizer). The object raises the reference's buffer error instead."""
+    p = ol.default_params(window_size=480, shift=124, num_banks=32, low_freq=120.0, high_freq=6800.0, ceps_len=13)
+    x = synth_utterances(1, 41312, seed=1033)[0]
+    with pytest.raises(afe.AfeError, match="buffer is too small"):
+        afe.extract_stream(to_afe_params(p, 16000), x)
+    got = afe.extract_stream(to_afe_params(p, BIG), x)          # one block: fine
+    assert got.shape[0] == (len(x) - (480 - 124)) // 124 and np.isfinite(got).all()
+
+
 def test_stream_reset_makes_handle_reusable(oracle):
     pcm = load_pcm()
     p = ol.default_params(dyn="acc", norm="cmn")
