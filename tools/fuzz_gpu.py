@@ -3,6 +3,7 @@
 regression widths, normalisation kind and order, VTLN alpha, pre-set block sizes) x ragged utterances, the fused batch path and
 the streaming object against the reference's own CPU classes (oracle/_ref, or the C port). The fixed cases live in tests/; this
 looks for parameter corners they do not name. Usage (under gpurun): python tools/fuzz_gpu.py [n_cases] [seed]
+`python tools/fuzz_gpu.py schemes [n] [seed]`: bitwise equality of the normalisation / staging routes on random ragged batches.
 Prints one line per failure and a summary; exit code 1 when any case is out of tolerance."""
 import os
 import sys
@@ -104,7 +105,47 @@ def isolated(fn, *args):
     return res[1]
 
 
+def schemes(n_cases, seed):
+    """Internal consistency: the same random batch (ragged lengths from the minimum to 30 s, so clusters of 1-4 tiles, the ticket
+    scheme and the role scheme all occur) through every normalisation route and staging path must give the SAME BITS."""
+    rng = np.random.default_rng(seed)
+    fails, done, skipped = [], 0, 0
+    for case in range(n_cases):
+        p = random_params(rng)
+        p["norm"] = int(rng.integers(1, 4))
+        if p["shift"] % 2:
+            p["shift"] += 1
+        D = p["delta_l1"] + p["delta_l2"] if p["dyn"] else 0
+        n_min = p["window_size"] + p["shift"] * (2 * D + 4)
+        lens = [n_min, int(rng.integers(n_min, 20000)), int(rng.integers(20000, 200000)), int(rng.integers(100000, 480000)),
+                int(rng.integers(n_min, 60000)), int(rng.integers(200000, 330000))]
+        rng.shuffle(lens)
+        utts = [synth_utterances(1, n, seed=5000 + 10 * case + i, sr=p["sample_rate"])[0] for i, n in enumerate(lens)]
+        scope = int(rng.integers(0, 2))
+        try:
+            base = run_batch(p, utts, stats_scope=scope)
+            for name, fl in (("no_cluster", afe.BATCH_NO_CLUSTER), ("unfused", afe.BATCH_UNFUSED_NORM), ("no_tma", afe.BATCH_NO_TMA),
+                             ("q1", afe.BATCH_Q1_EXACT)):
+                other = run_batch(p, utts, stats_scope=scope, flags=fl)
+                for i, (a, b) in enumerate(zip(base, other)):
+                    same = np.array_equal(a, b, equal_nan=True) if name != "q1" else np.array_equal(a[:max(0, len(a) - D)], b[:max(0, len(b) - D)], equal_nan=True)
+                    if not same:
+                        fails.append(f"schemes case {case} {name} utt {i} (len {lens[i]}) differs: {p}")
+            done += 1
+        except afe.AfeError as e:
+            if "fused path" in str(e) or "mel filter" in str(e) or "window" in str(e):
+                skipped += 1
+            else:
+                fails.append(f"schemes case {case}: {e} {p}")
+    for f in fails:
+        print("FAIL", f)
+    print(f"fuzz schemes: {done} batches x 5 routes, {skipped} skipped, {len(fails)} failures, seed {seed}")
+    return 1 if fails else 0
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "schemes":
+        return schemes(int(sys.argv[2]) if len(sys.argv) > 2 else 60, int(sys.argv[3]) if len(sys.argv) > 3 else 11)
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 120
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 2026
     rng = np.random.default_rng(seed)
