@@ -546,12 +546,55 @@ def leg_stream_object(cx, pcm, n_files=64, threads=(1, 4)):
                 cpp[f"{nt}_threads"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-200:]}
             except Exception as e:
                 cpp[f"{nt}_threads"] = {"error": str(e)[:200]}
+    online = online_blocks(cx, host[0])
     best = max([v["frames_per_s"] for v in out.values()] + [v.get("frames_per_s", 0.0) for v in cpp.values()])
-    return {"value": best, "unit": UNIT, "python_threads": out, "cpp_threads_parambase_ptr": cpp, "files": n_files,
+    return {"value": best, "unit": UNIT, "python_threads": out, "cpp_threads_parambase_ptr": cpp, "online_200ms_blocks": online, "files": n_files,
             "uses_fused_kernel": bool(fused),
             "api": "MfccCuda through the reference's verbs (set_input / set_alpha / apply / get_output_data / flush) per 10 s file, host "
                    "buffers in and out; one object per host thread",
             "first_file_rows": int(check.shape[0])}
+
+
+def online_blocks(cx, u, block=3200):
+    """The same object as an ONLINE front end: a 10 s file arrives in 200 ms blocks (set_input -> apply -> get_output_data per
+    block, one launch of the fused kernel each); latency of a block from host buffer to host rows, and the rows against the
+    reference's CPU object fed the same blocks (per-block CMN statistics, Q2)."""
+    afe = cx.afe
+    g = CFG16
+    p = params_dict()
+    ap = afe.make_params(input_buffer_size=block, **{k: v for k, v in p.items() if k != "alpha"})
+    m = afe.MfccCuda(ap, cx.local)
+    m.set_window(afe.make_window(g["W"]))
+    limit = block
+    block = m.get_input_buffer_size()                         # whole frames: est(limit) * S + W - S, as the reference driver feeds it
+    lat, rows = [], []
+    for rep in range(3):                                      # the last pass is reported
+        lat, rows = [], []
+        for pos in range(0, len(u), block):
+            t0 = time.perf_counter()
+            wc = m.set_input(u[pos:pos + block]); m.apply()
+            r = m.get_output_data(wc) if wc > 0 else None
+            lat.append(time.perf_counter() - t0)
+            if r is not None:
+                rows.append(r)
+        wc = m.flush(); m.apply()
+        if wc > 0:
+            rows.append(m.get_output_data(wc))
+        m.reset()
+    m.close()
+    got = np.concatenate(rows)
+    res = {"block_samples": block, "blocks": len(lat), "us_per_block_median": float(np.median(lat) * 1e6),
+           "us_per_block_max": float(np.max(lat) * 1e6), "real_time_factor": float(np.sum(lat) / (len(u) / g["sr"])),
+           "rows": int(got.shape[0])}
+    try:
+        import oracle_lib as ol
+        lib = ol.RefLib("ref" if ol.available("ref") else "port")
+        want = lib.extract(p, [u], sample_limit=limit)[0][0]
+        res["max_abs_vs_reference_same_blocks"] = float(np.abs(got - want).max()) if got.shape == want.shape else None
+        res["rows_reference"] = int(want.shape[0])
+    except Exception as e:  # noqa: BLE001
+        res["reference_error"] = str(e)[:200]
+    return res
 
 
 def leg_config5(cx, args, steps):
