@@ -151,7 +151,7 @@ void count_launch(int n) { g_launches.fetch_add(n); }
 // ------------------------------------------------------------------------------------------------ K1 launch table
 #define AFE_DECL_INST(k) cudaError_t fused_launch_##k(const FusedLaunch &); int fused_max_clusters_##k(const FusedLaunch &);
 #define AFE_FOR_EACH_INST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) \
-    X(18) X(19) X(20) X(21) X(22) X(23)
+    X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25)
 AFE_FOR_EACH_INST(AFE_DECL_INST)
 #undef AFE_DECL_INST
 
@@ -237,7 +237,95 @@ FusedEngine::FusedEngine(const Derived &dd, int dev) : d(dd), device(dev)
     const int kf = (d.nb + 7) / 8;     // filters per warp (8 warps): instantiated for 3, 5 and 8
     key = (d.N2 == 512 ? 0 : 6) + (pruned ? 0 : 3) + (kf <= 3 ? 0 : kf <= 5 ? 1 : 2);
 }
-FusedEngine::~FusedEngine() { fft.release(); mel.release(); }
+FusedEngine::~FusedEngine()
+{
+    fft.release(); mel.release();
+    if (d_bfrag) cudaFree(d_bfrag);
+    if (d_dfrag) cudaFree(d_dfrag);
+}
+
+// TF32 with round-to-nearest-away of the 13 dropped mantissa bits (cvt.rna.tf32.f32)
+static float tf32_rna(float x)
+{
+    uint32_t u; memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r; memcpy(&r, &u, 4);
+    return r;
+}
+static float4 split_pair(float b0, float b1)
+{
+    const float h0 = tf32_rna(b0), h1 = tf32_rna(b1);
+    return make_float4(h0, h1, tf32_rna(b0 - h0), tf32_rna(b1 - h1));
+}
+
+// Fragment tables of the tensor-core phase 2 for the mel tables at hand (mc_alpha): the band of the mel matrix per filter
+// tile j (8 filters) in steps of 8 bins, the DCT matrix per (filter tile, column tile), and the deal of the units
+// (half round, filter tile) to the 8 warps (longest first onto the least loaded warp, at most two per warp).
+void FusedEngine::ensure_mma(cudaStream_t st)
+{
+    if (mma_alpha == mc_alpha && d_bfrag) return;
+    std::vector<int> edges; std::vector<float> filters, dct;
+    build_filters(d, mc_alpha, edges, filters);
+    const int nt = (d.nb + 7) / 8;
+    const float scale = 0.5f / (float)d.N2;
+    std::vector<int> s0(nt), ns(nt), boff(nt);
+    int rows = 0;
+    for (int j = 0; j < nt; j++) {
+        const int fb = 8 * j, fl = std::min(8 * j + 7, d.nb - 1);
+        s0[j] = edges[fb] / 8;
+        ns[j] = std::max(1, (edges[fl + 2] + 7) / 8 - s0[j]);
+        if (8 * (s0[j] + ns[j]) > kMagStride + 16 || ns[j] > 255) throw Error("mel filter tile too wide for the tensor-core phase 2");
+        boff[j] = rows; rows += ns[j];
+    }
+    std::vector<float4> bfrag((size_t)rows * 32), dfrag((size_t)nt * 2 * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+    auto W = [&](int bin, int f) -> float {          // mel matrix entry (bin, filter), mfcccpu.cpp:24-60 tables
+        if (f >= d.nb || bin < edges[f] || bin >= edges[f + 2] || bin >= d.N2) return 0.f;
+        return filters[(size_t)(f % 2) * d.N2 + bin] * scale;
+    };
+    for (int j = 0; j < nt; j++)
+        for (int s = 0; s < ns[j]; s++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t = lane & 3, bin = 8 * (s0[j] + s);
+                bfrag[((size_t)boff[j] + s) * 32 + lane] = split_pair(W(bin + t, 8 * j + g), W(bin + t + 4, 8 * j + g));
+            }
+    if (d.C > 0) {
+        build_dct(d, dct);
+        auto D = [&](int f, int c) -> float { return f < d.nb && c < d.dct_len ? dct[(size_t)f * d.dct_len + c] : 0.f; };
+        for (int j = 0; j < nt; j++)
+            for (int ct = 0; ct < 2; ct++)
+                for (int lane = 0; lane < 32; lane++) {
+                    const int g = lane >> 2, t = lane & 3;  // k = t <-> filter 8j + 2t, k = t + 4 <-> filter 8j + 2t + 1
+                    dfrag[((size_t)j * 2 + ct) * 32 + lane] = split_pair(D(8 * j + 2 * t, 8 * ct + g), D(8 * j + 2 * t + 1, 8 * ct + g));
+                }
+    }
+    // deal the 2 * nt units
+    struct Unit { int m, j, cost; };
+    std::vector<Unit> units;
+    for (int j = 0; j < nt; j++) for (int m = 0; m < 2; m++) units.push_back({m, j, ns[j] * 18 + 100});
+    std::stable_sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) { return x.cost > y.cost; });
+    int load[8] = {0}, cnt[8] = {0};
+    for (int w = 0; w < 8; w++) for (int i = 0; i < 2; i++) { mc.mma_unit[w][i] = -1; mc.mma_boff[w][i] = 0; }
+    for (const Unit &u : units) {
+        int best = -1;
+        for (int w = 0; w < 8; w++) if (cnt[w] < 2 && (best < 0 || load[w] < load[best])) best = w;
+        if (best < 0) throw Error("tensor-core phase 2: more than 16 units");
+        mc.mma_unit[best][cnt[best]] = u.m | (u.j << 4) | (s0[u.j] << 8) | (ns[u.j] << 16);
+        mc.mma_boff[best][cnt[best]] = boff[u.j];
+        cnt[best]++; load[best] += u.cost;
+    }
+    if (rows > (int)bfrag_rows || !d_bfrag) {
+        if (d_bfrag) cudaFree(d_bfrag);
+        if (d_dfrag) cudaFree(d_dfrag);
+        AFE_CUDA(cudaMalloc(&d_bfrag, sizeof(float4) * 32 * (size_t)rows));
+        AFE_CUDA(cudaMalloc(&d_dfrag, sizeof(float4) * 32 * (size_t)kMaxBanks / 8 * 2));
+        bfrag_rows = rows;
+    }
+    // pageable sources: the copies are staged before the calls return, and they are ordered on `st` before the launch
+    AFE_CUDA(cudaMemcpyAsync(d_bfrag, bfrag.data(), sizeof(float4) * bfrag.size(), cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaMemcpyAsync(d_dfrag, dfrag.data(), sizeof(float4) * dfrag.size(), cudaMemcpyHostToDevice, st));
+    AFE_CUDA(cudaStreamSynchronize(st));
+    mma_alpha = mc_alpha;
+}
 
 void FusedEngine::set_window(const float *window, cudaStream_t st)
 {
@@ -246,14 +334,15 @@ void FusedEngine::set_window(const float *window, cudaStream_t st)
 }
 void FusedEngine::ensure_mel(float alpha)
 {
-    if (mc_alpha != alpha) { build_mel_const(d, alpha, mc); mc_alpha = alpha; }
+    if (mc_alpha != alpha) { build_mel_const(d, alpha, mc); mc_alpha = alpha; mma_alpha = -1.f; }
 }
 std::string FusedEngine::kernel_label() const
 {
     const int kf = (d.nb + 7) / 8;
     char buf[96];
-    snprintf(buf, sizeof buf, "k_fused_mfcc<%d,%d,8,%d,%s>", d.N2, pruned ? 13 : 16, kf <= 3 ? 3 : kf <= 5 ? 5 : 8,
-             pre != 0.f ? "true" : "false");
+    if (mma_active()) snprintf(buf, sizeof buf, "k_fused_mfcc<%d,13,8,5,false,MMA>", d.N2);
+    else snprintf(buf, sizeof buf, "k_fused_mfcc<%d,%d,8,%d,%s>", d.N2, pruned ? 13 : 16, kf <= 3 ? 3 : kf <= 5 ? 5 : 8,
+                  pre != 0.f ? "true" : "false");
     return buf;
 }
 
@@ -339,8 +428,15 @@ bool FusedEngine::cluster_schedulable(int cluster, const FusedArgs &a, cudaStrea
 void FusedEngine::launch(const FusedArgs &a, int grid, int cluster, cudaStream_t st)
 {
     if (!window_set) throw Error("set_window must be called before running");
-    FusedLaunch fl{a, L, &mc, grid, cluster, st};
-    const cudaError_t e = launch_fused_variant(key + (a.pre != 0.f ? 12 : 0), fl);
+    FusedArgs am = a;
+    int k = key + (a.pre != 0.f ? 12 : 0);
+    if (mma_active()) {
+        ensure_mma(st);
+        am.mma_bfrag = d_bfrag; am.mma_dfrag = d_dfrag;
+        k = d.N2 == 512 ? 24 : 25;
+    }
+    FusedLaunch fl{am, L, &mc, grid, cluster, st};
+    const cudaError_t e = launch_fused_variant(k, fl);
     if (e != cudaSuccess) {
         cudaGetLastError();
         throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at k_fused_mfcc launch" + (cluster > 0 ? " (clustered)" : ""));
@@ -435,6 +531,7 @@ static void run_extract(afe_batch *b, const int16_t *d_pcm, float *d_out, int t0
     if (t1 <= t0) return;
     if (!b->d_tiles) throw Error("afe_batch_plan must be called before running");
     FusedEngine &eng = *b->eng;
+    eng.want_mma = (b->flags & AFE_BATCH_MMA_PHASE2) != 0;
     eng.ensure_mel(b->alpha);
     const Derived &d = b->d;
     const bool want_stats = d.p.norm != AFE_NORM_NONE;
@@ -738,6 +835,7 @@ int afe_batch_kernel_launches(const afe_batch *b) { return b->last_launches; }
 const char *afe_batch_kernel_name(const afe_batch *b)
 {
     static thread_local std::string name;
+    if (b->eng) b->eng->want_mma = (b->flags & AFE_BATCH_MMA_PHASE2) != 0;
     name = b->eng ? b->eng->kernel_label() : "k_fused_mfcc";
     return name.c_str();
 }

@@ -670,7 +670,8 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     cx.barrier, cx.max_over_ranks = barrier, max_over_ranks
-    cx.flags = afe.BATCH_Q1_EXACT | (afe.BATCH_NO_TMA if args.no_tma else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0)
+    cx.flags = (afe.BATCH_Q1_EXACT | (afe.BATCH_NO_TMA if args.no_tma else 0) | (afe.BATCH_NO_CLUSTER if args.no_cluster else 0)
+                | (afe.BATCH_MMA_PHASE2 if args.mma else 0))
     cx.ap16 = afe.make_params(input_buffer_size=1 << 22, **{k: v for k, v in params_dict().items() if k != "alpha"})
     # a dedicated (non-default) stream: the library launches on it and the CUDA events are recorded on it
     cx.stream = torch.cuda.Stream(device=cx.dev)
@@ -814,6 +815,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin ranks to their GPU's NUMA node (A/B, N > 1)")
     ap.add_argument("--no-cluster", action="store_true", help="ticket-scheme normalisation instead of clusters + DSMEM (A/B)")
     ap.add_argument("--no-tma", action="store_true")
+    ap.add_argument("--mma", action="store_true", help="mel + log + DCT on the tensor cores (AFE_BATCH_MMA_PHASE2) instead of CUDA cores (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-4 / config-5 / stream-object extra blocks")

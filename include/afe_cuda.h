@@ -181,8 +181,10 @@ enum afe_batch_flags {
     AFE_BATCH_Q1_EXACT = 1,        /* reproduce the single-block flush quirk Q1 (statics of the last D rows) */
     AFE_BATCH_NO_TMA = 2,          /* stage PCM with plain vector loads instead of cp.async.bulk (debug / A-B test) */
     AFE_BATCH_UNFUSED_NORM = 8,    /* normalise with the separate K2/K3 kernels instead of inside the fused kernel (A-B test) */
-    AFE_BATCH_NO_CLUSTER = 32      /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
+    AFE_BATCH_NO_CLUSTER = 32,     /* fused normalisation through the ticket scheme (last tile of an utterance normalises it in
                                       place via L2) instead of thread-block clusters + distributed shared memory (A-B test) */
+    AFE_BATCH_MMA_PHASE2 = 64      /* mel + log + DCT on the tensor cores (mma.sync m16n8k8, 3xTF32 split, FP32 accumulate) instead of
+                                      the CUDA-core FMA phase; same tolerance, not the same bits (A-B test) */
 };
 
 int afe_batch_create(const afe_params *p, int cuda_device, afe_batch **out);

@@ -294,6 +294,30 @@ def test_batch_is_deterministic_and_order_independent():
         np.testing.assert_array_equal(a[i], e[i])
 
 
+@pytest.mark.parametrize("cfg", [dict(num_banks=40), dict(num_banks=23), dict(num_banks=64),
+                                 dict(num_banks=20, window_size=200, shift=80, sample_rate=8000.0, high_freq=4000.0),
+                                 dict(num_banks=40, ceps_len=0, want_c0=0), dict(num_banks=26, ceps_len=15, want_c0=1)])
+def test_batch_tensor_core_phase2_matches_oracle(oracle, cfg):
+    """AFE_BATCH_MMA_PHASE2: mel sums and DCT as mma.sync m16n8k8 products with 3xTF32 operands (FP32 accumulate) instead of the
+    CUDA-core FMA phase. Not the same bits (different summation order, split operands) but the same stated tolerance against the
+    reference's CPU classes, and within 1e-4 of the default kernel; VTLN-warped banks and ragged lengths included."""
+    p = ol.default_params(norm="cmn", dyn="acc", **cfg)
+    utts = synth_utterances(10, 60000, seed=51, sr=p["sample_rate"], ragged=True)
+    for alpha in (1.0, 0.9):
+        q = dict(p, alpha=alpha)
+        a = run_batch(q, utts, flags=afe.BATCH_Q1_EXACT | afe.BATCH_MMA_PHASE2)
+        b = run_batch(q, utts, flags=afe.BATCH_Q1_EXACT)
+        want = oracle_extract(oracle, q, utts, BIG)
+        for i in range(len(utts)):
+            assert_close(a[i], want[i], q, f"mma phase 2 utt {i} alpha {alpha}")
+            assert np.abs(a[i] - b[i]).max() < 1e-4
+    bm = afe.BatchMfcc(to_afe_params(p, BIG), 0, flags=afe.BATCH_MMA_PHASE2)
+    try:
+        assert bm.kernel_name.endswith("MMA>"), bm.kernel_name
+    finally:
+        bm.close()
+
+
 @pytest.mark.parametrize("norm", ["cmn", "cvn", "minmax"])
 def test_batch_cluster_normalisation_equals_ticket_scheme(norm):
     """Fused normalisation inside a thread-block cluster (one cluster = the 1 or 2 tiles of an utterance, statistics
